@@ -1,0 +1,134 @@
+/* umr_b200.h -- C ABI of libumr_b200.so: B200 (sm_100a) soft rasteriser + geometric-loss kernels.
+ *
+ * This is the drop-in boundary for the hot path of NVlabs/UMR.  Each entry point
+ * replaces a reference interface, cited as file:line under the reference tree:
+ *
+ *   umr_raster_forward / umr_raster_backward
+ *       replace the pybind functions `forward_soft_rasterize` / `backward_soft_rasterize` of
+ *       external/SoftRas/soft_renderer/cuda/soft_rasterize_cuda.cpp:62-97 / :100-138 (kernels
+ *       soft_rasterize_cuda_kernel.cu:222-282, :285-476, :479-656) AND the host work around them in
+ *       functional/soft_rasterize.py:41-73,94-106 (buffer fills, `grid`, p2f normalisation) and
+ *       rasterizer.py:52-53 (2x2 average pool), which are fused into the kernels.
+ *   umr_bilinear_sample_forward / _backward
+ *       replace `F.grid_sample` (+permute) at nnutils/geom_utils.py:41-59 and
+ *       nnutils/loss_utils.py:59-64 (torch-1.1 semantics == align_corners=True, zeros padding).
+ *   umr_iou_forward / _backward      replace nnutils/loss_utils.py:41-48 (`neg_iou_loss`).
+ *   umr_chamfer_forward / _backward  replace nnutils/chamfer_python.py:43-64 (`distChamfer`).
+ *   umr_texcycle_forward / _backward replace nnutils/loss_utils.py:152-182 (`TexCycle.forward`).
+ *
+ * Conventions: plain device pointers + sizes, no torch types.  Every buffer is CALLER-allocated
+ * (torch owns all memory); the library keeps no global mutable state and is re-entrant across host
+ * threads and devices (the device is the current CUDA device of the calling thread).  All work is
+ * enqueued asynchronously on `stream` (a cudaStream_t passed as void*).  Return value: 0 on success,
+ * a positive cudaError_t, or a negative UMR_ERR_* code; umr_error_string() decodes both.  Nothing
+ * is ever printed (the reference only printf()s launch failures, kernel.cu:700-702,734-736,799-801).
+ */
+#ifndef UMR_B200_H_
+#define UMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMR_OK 0
+#define UMR_ERR_UNSUPPORTED (-1) /* mode combination not built into the sm_100a kernels        */
+#define UMR_ERR_BAD_ARG (-2)     /* null pointer / non-positive size / misaligned buffer       */
+#define UMR_ERR_TOO_LARGE (-3)   /* size beyond a compiled limit (e.g. num_faces > 65535)      */
+
+/* mode ids: same numbering as functional/soft_rasterize.py:22-25 */
+enum { UMR_DIST_HARD = 0, UMR_DIST_BARYCENTRIC = 1, UMR_DIST_EUCLIDEAN = 2 };
+enum { UMR_RGB_HARD = 0, UMR_RGB_SOFTMAX = 1 };
+enum { UMR_ALPHA_HARD = 0, UMR_ALPHA_SUM = 1, UMR_ALPHA_PROD = 2 };
+enum { UMR_TEX_SURFACE = 0, UMR_TEX_VERTEX = 1 };
+
+/* Scalar arguments of soft_rasterize (soft_rasterize_cuda.cpp:71-82), plus the fused-host-work
+ * fields.  `dist_eps` is the ALREADY TRANSFORMED value log(1/dist_eps - 1) the reference binding
+ * receives (functional/soft_rasterize.py:35). */
+typedef struct UmrRasterParams {
+    int32_t batch_size;    /* B */
+    int32_t num_faces;     /* F (<= 65535) */
+    int32_t texture_size;  /* T2 = texture_res^2 (surface textures [B,F,T2,3]) */
+    int32_t image_size;    /* output image side `is`; raster side S = is * (anti_aliasing ? 2 : 1) */
+    int32_t anti_aliasing; /* 1: rasterise at 2*is and 2x2 average-pool (rasterizer.py:43,52-53) */
+    float near_plane, far_plane, eps, sigma_val, dist_eps, gamma_val;
+    int32_t func_id_dist, func_id_rgb, func_id_alpha, texture_sample_type, double_side;
+    float background_color[3];
+} UmrRasterParams;
+
+const char* umr_error_string(int code);
+int umr_version(void);
+
+/* Bytes of scratch `workspace` umr_raster_forward/backward need (256-byte aligned device memory). */
+size_t umr_raster_workspace_bytes(int32_t batch_size, int32_t num_faces);
+
+/* Forward.  face_vertices [B,F,9] f32 (x0,y0,z0,x1,...), textures [B,F,T2,3] f32.
+ * Outputs (all fully written, no pre-fill needed):
+ *   images      [B,4,is,is]   pooled RGBA (== soft_colors when anti_aliasing == 0)
+ *   soft_colors [B,4,S,S]     un-pooled RGBA, needed by backward; may be NULL when anti_aliasing==0
+ *                             (images is then the un-pooled tensor) or when no backward will follow
+ *   aggrs_info  [B,2,S,S]     softmax: (sum, max); hard: (depth_min, float(face_index_min))
+ *   p2f_info    [B,F,2]       normalised pixel->face affinity (zeros in hard mode); may be NULL */
+int umr_raster_forward(const float* face_vertices, const float* textures, float* images,
+                       float* soft_colors, float* aggrs_info, float* p2f_info,
+                       const UmrRasterParams* params, void* workspace, void* stream);
+
+/* Backward.  grad_images [B,4,is,is] is the gradient w.r.t. `images` (the 2x2 pool backward is
+ * fused).  Outputs are zero-filled by the call, then accumulated:
+ *   grad_faces    [B,F,9]
+ *   grad_textures [B,F,T2,3]  may be NULL (skips the texture gradient, e.g. silhouette renders)
+ * Only the sampled texel receives texture gradient (intended semantics of kernel.cu:199-218; the
+ * reference's uninitialised-variable behaviour is NOT reproduced -- SURVEY.md App. B-1). */
+int umr_raster_backward(const float* face_vertices, const float* textures, const float* soft_colors,
+                        const float* aggrs_info, const float* grad_images, float* grad_faces,
+                        float* grad_textures, const UmrRasterParams* params, void* workspace,
+                        void* stream);
+
+/* Bilinear sampler, align_corners=True, zeros padding (geom_utils.py:41-59, loss_utils.py:59-64).
+ * image [B,C,H,W], flow [B,N,2] (x,y in [-1,1]) -> out [B,N,C] (i.e. already permuted to the
+ * `B x F x T x T x C` order sample_textures returns).  Backward: gradient w.r.t. flow only
+ * (grad_flow [B,N,2], fully written) -- and optionally w.r.t. image (grad_image [B,C,H,W],
+ * zero-filled by the call then accumulated; NULL to skip). */
+int umr_bilinear_sample_forward(const float* image, const float* flow, float* out, int32_t B,
+                                int32_t C, int32_t H, int32_t W, int32_t N, void* stream);
+int umr_bilinear_sample_backward(const float* image, const float* flow, const float* grad_out,
+                                 float* grad_flow, float* grad_image, int32_t B, int32_t C,
+                                 int32_t H, int32_t W, int32_t N, void* stream);
+
+/* neg_iou_loss (loss_utils.py:41-48).  predict/target [B,N] -> inter[B], uni[B] (uni includes the
+ * +1e-6) and loss[B] = 1 - inter/uni.  Backward: grad_predict[B,N] = grad_loss[b] * dloss/dp. */
+int umr_iou_forward(const float* predict, const float* target, float* inter, float* uni,
+                    float* loss, int32_t B, int64_t N, void* stream);
+int umr_iou_backward(const float* target, const float* inter, const float* uni,
+                     const float* grad_loss, float* grad_predict, int32_t B, int64_t N,
+                     void* stream);
+
+/* distChamfer (chamfer_python.py:43-64) for D == 2 or 3.  a [B,N,D], b [B,M,D] ->
+ * dist_ab[B,N], dist_ba[B,M], idx_ab[B,N] (int32), idx_ba[B,M] (int32), using the reference's
+ * expanded form |a|^2 + |b|^2 - 2 a.b and lowest-index tie-breaking.
+ * Backward: grad_a[B,N,D], grad_b[B,M,D] from grad_dist_ab / grad_dist_ba (either may be NULL). */
+int umr_chamfer_forward(const float* a, const float* b, float* dist_ab, float* dist_ba,
+                        int32_t* idx_ab, int32_t* idx_ba, int32_t B, int32_t N, int32_t M,
+                        int32_t D, void* stream);
+int umr_chamfer_backward(const float* a, const float* b, const int32_t* idx_ab,
+                         const int32_t* idx_ba, const float* grad_dist_ab,
+                         const float* grad_dist_ba, float* grad_a, float* grad_b, int32_t B,
+                         int32_t N, int32_t M, int32_t D, void* stream);
+
+/* TexCycle (loss_utils.py:152-182).  flow [B,F,T2,2], prob [B,F,2], face_ids [B,P] (the hard
+ * renderer's aggrs_info[:,1] plane as float, -1 = background which marks face F-1 visible like the
+ * reference's negative index does).  visible [B,F] (uint8 scratch, written), loss[1].
+ * Backward: grad_flow [B,F,T2,2] = grad_loss * dloss/dflow. */
+int umr_texcycle_forward(const float* flow, const float* prob, const float* face_ids,
+                         uint8_t* visible, float* loss, int32_t B, int32_t F, int32_t T2,
+                         int64_t P, void* stream);
+int umr_texcycle_backward(const float* flow, const float* prob, const uint8_t* visible,
+                          const float* grad_loss, float* grad_flow, int32_t B, int32_t F,
+                          int32_t T2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMR_B200_H_ */

@@ -1,0 +1,90 @@
+"""GPU parity: the sm_100a rasteriser (through the C ABI / autograd binding) vs CPU oracle B on the
+same seeded inputs.  Tolerance: 1e-4 relative fp32 (BASELINE.json north_star); the hard-mode
+face-index plane and depth plane bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import softras  # oracle (test infrastructure)
+from umr_b200 import raster
+from util import rel_report, scene
+
+pytestmark = pytest.mark.gpu
+
+UMR = dict(sigma_val=1e-5, dist_eps=1e-10, gamma_val=1e-4, eps=1e-3, near=1, far=100, fill_back=True)
+
+
+def run_gpu(fv, tex, image_size, aa, rgb, grad_img=None, tex_grad=True):
+    dev = torch.device("cuda:0")
+    tfv = torch.from_numpy(fv).to(dev).requires_grad_(grad_img is not None)
+    ttex = torch.from_numpy(tex).to(dev).requires_grad_(grad_img is not None and tex_grad)
+    img, p2f, aggr = raster.soft_rasterize(tfv, ttex, image_size, aggr_func_rgb=rgb, anti_aliasing=aa, **UMR)
+    out = dict(images=img.detach().cpu().numpy(), p2f=p2f.cpu().numpy(), aggrs=aggr.cpu().numpy())
+    if grad_img is not None:
+        img.backward(torch.from_numpy(grad_img).to(dev))
+        out["grad_faces"] = tfv.grad.cpu().numpy()
+        out["grad_tex"] = ttex.grad.cpu().numpy() if tex_grad else None
+    torch.cuda.synchronize()
+    return out
+
+
+def run_oracle(fv, tex, image_size, aa, rgb, grad_img=None):
+    img, fwd, cfg = softras.render(fv, tex, image_size, anti_aliasing=aa, impl="B", aggr_func_rgb=rgb,
+                                   sigma_val=1e-5, dist_eps=1e-10, gamma_val=1e-4)
+    out = dict(images=img, p2f=fwd["p2f_info"], aggrs=fwd["aggrs_info"], soft_colors=fwd["soft_colors"])
+    if grad_img is not None:
+        gf, gt = softras.render_backward(fwd, cfg, grad_img, anti_aliasing=aa, impl="B", nthreads=0)
+        out["grad_faces"], out["grad_tex"] = gf, gt
+    return out
+
+
+CASES = [
+    # (B, subdiv, tex_res, image_size, aa, rgb)
+    (2, 3, 2, 64, True, "softmax"),
+    (2, 3, 2, 64, True, "hard"),
+    (1, 3, 6, 128, True, "softmax"),
+    (2, 3, 1, 64, False, "softmax"),
+    (1, 2, 3, 50, False, "hard"),     # S not a multiple of the tile
+    (1, 2, 3, 37, True, "softmax"),   # odd output size, S = 74
+]
+
+
+@pytest.mark.parametrize("B,subdiv,tex_res,image_size,aa,rgb", CASES)
+def test_forward_backward_parity(B, subdiv, tex_res, image_size, aa, rgb):
+    fv, tex = scene(B, subdiv, tex_res, seed=B * 100 + image_size)
+    g = np.random.default_rng(7).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
+    ref = run_oracle(fv, tex, image_size, aa, rgb, g)
+    got = run_gpu(fv, tex, image_size, aa, rgb, g)
+    msgs, ok = [], True
+    for k, rt, at in [("images", 1e-4, 1e-6), ("aggrs", 1e-4, 1e-6), ("p2f", 1e-4, 1e-6),
+                      ("grad_faces", 1e-4, 1e-5), ("grad_tex", 1e-4, 1e-6)]:
+        if k == "grad_faces":  # atomics-order tolerance scaled to the tensor magnitude
+            at = 1e-6 * float(np.abs(ref[k]).max() + 1e-30) + 1e-7
+        o, m = rel_report(k, got[k], ref[k], rt, at)
+        ok &= o
+        msgs.append(m)
+    if rgb == "hard":
+        exact = np.array_equal(got["aggrs"], ref["aggrs"])
+        msgs.append("hard aggrs (depth, face-id) bit-exact: %s" % exact)
+        ok &= exact
+    print("\n".join(msgs))
+    assert ok, "\n" + "\n".join(msgs)
+
+
+def test_no_texture_grad_and_no_grad_paths():
+    fv, tex = scene(2, 3, 1, seed=3)
+    g = np.random.default_rng(8).normal(size=(2, 4, 64, 64)).astype(np.float32)
+    ref = run_oracle(fv, tex, 64, True, "softmax", g)
+    got = run_gpu(fv, tex, 64, True, "softmax", g, tex_grad=False)
+    at = 1e-6 * float(np.abs(ref["grad_faces"]).max()) + 1e-7
+    ok, msg = rel_report("grad_faces(no texgrad)", got["grad_faces"], ref["grad_faces"], 1e-4, at)
+    assert ok, msg
+    got2 = run_gpu(fv, tex, 64, True, "softmax", None)
+    ok, msg = rel_report("images(no grad)", got2["images"], ref["images"], 1e-4, 1e-6)
+    assert ok, msg
+
+
+def test_cpu_tensor_raises():
+    fv, tex = scene(1, 2, 1)
+    with pytest.raises(TypeError):
+        raster.soft_rasterize(torch.from_numpy(fv), torch.from_numpy(tex), 32)

@@ -1,0 +1,47 @@
+"""Ad-hoc kernel timing (CUDA events) of the raster forward/backward at a given config."""
+import argparse
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from umr_b200 import raster, synth
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=16)
+    ap.add_argument("--is", dest="isz", type=int, default=256)
+    ap.add_argument("--subdiv", type=int, default=3)
+    ap.add_argument("--R", type=int, default=6)
+    ap.add_argument("--rgb", default="softmax")
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    rng = np.random.default_rng(0)
+    v, f = synth.icosphere(a.subdiv)
+    verts = synth.bird_like(v, rng, a.B)
+    cams = synth.cameras(rng, a.B)
+    fv = torch.from_numpy(synth.raster_space_faces(verts, f, cams)).cuda().requires_grad_(True)
+    tex = torch.rand(a.B, f.shape[0], a.R * a.R, 3, device="cuda").requires_grad_(True)
+    g = torch.randn(a.B, 4, a.isz, a.isz, device="cuda")
+    kw = dict(sigma_val=1e-5, dist_eps=1e-10, gamma_val=1e-4, aggr_func_rgb=a.rgb, anti_aliasing=True)
+    for _ in range(3):
+        img, _, _ = raster.soft_rasterize(fv, tex, a.isz, **kw)
+        img.backward(g)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tf = tb = 0.0
+    for _ in range(a.iters):
+        e[0].record()
+        img, _, _ = raster.soft_rasterize(fv, tex, a.isz, **kw)
+        e[1].record()
+        img.backward(g)
+        e[2].record()
+        torch.cuda.synchronize()
+        tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
+    tf /= a.iters; tb /= a.iters
+    print("B=%d is=%d F=%d T2=%d %s: fwd %.3f ms  bwd %.3f ms  -> %.0f img/s (fwd+bwd), alpha mean %.4f" % (
+        a.B, a.isz, f.shape[0], a.R * a.R, a.rgb, tf, tb, a.B / ((tf + tb) * 1e-3), img[:, 3].mean().item()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""ctypes binding of libumr_b200.so (C ABI declared in include/umr_b200.h).
+
+The product path FAILS LOUDLY when the CUDA library is missing: there is no CPU fallback here
+(the CPU oracle lives in oracle/ and is test infrastructure only).
+"""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libumr_b200.so")
+
+c_f32p = ctypes.c_void_p  # raw device pointers are passed as integers (tensor.data_ptr())
+
+
+class UmrRasterParams(ctypes.Structure):
+    _fields_ = [("batch_size", ctypes.c_int32), ("num_faces", ctypes.c_int32),
+                ("texture_size", ctypes.c_int32), ("image_size", ctypes.c_int32),
+                ("anti_aliasing", ctypes.c_int32),
+                ("near_plane", ctypes.c_float), ("far_plane", ctypes.c_float), ("eps", ctypes.c_float),
+                ("sigma_val", ctypes.c_float), ("dist_eps", ctypes.c_float), ("gamma_val", ctypes.c_float),
+                ("func_id_dist", ctypes.c_int32), ("func_id_rgb", ctypes.c_int32),
+                ("func_id_alpha", ctypes.c_int32), ("texture_sample_type", ctypes.c_int32),
+                ("double_side", ctypes.c_int32), ("background_color", ctypes.c_float * 3)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "umr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "umr_version": (ctypes.c_int, []),
+    "umr_raster_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "umr_raster_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
+                                                        ctypes.c_void_p]),
+    "umr_raster_backward": (ctypes.c_int, [c_f32p] * 7 + [ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
+                                                         ctypes.c_void_p]),
+    "umr_bilinear_sample_forward": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),
+    "umr_bilinear_sample_backward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),
+    "umr_iou_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "umr_iou_backward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "umr_chamfer_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
+    "umr_chamfer_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
+    "umr_texcycle_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_int64,
+                                                                                ctypes.c_void_p]),
+    "umr_texcycle_backward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class UmrLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises UmrLibraryError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise UmrLibraryError(
+                    "libumr_b200.so is not built (%s). Run `python -m umr_b200.build` "
+                    "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in EXPORTS.items():
+                fn = getattr(lib, name)  # AttributeError if the symbol is missing
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().umr_error_string(int(code))
+        raise RuntimeError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", code))

@@ -1,0 +1,819 @@
+// raster.cu -- tile-binned soft rasteriser (forward + backward) for sm_100a.
+//
+// Replaces the reference kernels external/SoftRas/soft_renderer/cuda/soft_rasterize_cuda_kernel.cu
+// :222-282 (prep), :285-476 (forward), :479-656 (backward), which run one thread per pixel over ALL
+// faces.  Design:
+//   k_prep      one thread per face -> a 128-byte face record (vertices, barycentric inverse, Gram
+//               matrix, cull box expanded by the sigmoid cut-off radius, obtuse/front flags) plus a
+//               compact float4 cull box used for binning.
+//   k_raster_*  one CTA per 16x16-pixel tile.  (1) all 256 threads scan the cull boxes of the image
+//               and ballot-compact the faces that touch the tile into an ORDER-PRESERVING index list
+//               (ascending face index is required: p2f prefix-max weights, hard z-buffer tie-break);
+//               (2) the list's 128-byte records are staged into shared memory by TMA bulk copies
+//               (cp.async.bulk + mbarrier, two stages, 32 records each) so the copy of chunk c+1
+//               overlaps the math of chunk c; (3) each thread walks the staged records for its pixel.
+//               Forward fuses the background fill, the p2f accumulation (warp-shuffle reduce -> one
+//               shared atomic per warp -> one global atomic per (tile, face)), and the 2x2 average
+//               pool (warp shuffles).  Backward fuses the pool backward and reduces the 9 per-face
+//               vertex gradients with warp shuffles + shared accumulators, flushing once per
+//               (tile, face) instead of the reference's 9 global atomics per (pixel, face).
+//
+// PARITY: this translation unit is compiled with -fmad=false.  The per-(pixel, face) arithmetic is an
+// operation-for-operation twin of the reference's float instantiation (same expression order, same
+// float/double promotions -- SURVEY.md App. B-6), because the reference's output is numerically
+// chaotic on sliver faces (App. B-15) and only an identical IEEE op sequence reproduces its discrete
+// decisions.  Only expf() may differ from a CPU libm by ulps.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "umr_b200.h"
+
+namespace umr {
+
+constexpr int TILE = 16;
+constexpr int CTA = TILE * TILE;  // 256 threads, one pixel each
+constexpr int CHUNK = 32;         // face records per TMA stage
+constexpr int NSTAGE = 2;
+constexpr int REC_F = 32;         // floats per record (128 B)
+
+// record layout (float index)
+constexpr int R_V = 0;     // 9 : x0 y0 z0 x1 y1 z1 x2 y2 z2
+constexpr int R_INV = 9;   // 9 : barycentric inverse, row-major
+constexpr int R_SYM = 18;  // 6 : s00 s01 s02 s11 s12 s22   (Gram + 1)
+constexpr int R_BOX = 24;  // 4 : xlo xhi ylo yhi (cull box, already expanded by r)
+constexpr int R_FLG = 28;  // 1 : bit0..2 obtuse corner, bit3 front-facing
+// 29..31 pad
+
+struct WorkspaceLayout {
+    size_t rec_off, box_off, p2f_off, total;
+};
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline WorkspaceLayout ws_layout(int B, int F) {
+    WorkspaceLayout L;
+    const size_t n = (size_t)B * F;
+    L.rec_off = 0;
+    L.box_off = align256(n * REC_F * sizeof(float));
+    L.p2f_off = L.box_off + align256(n * sizeof(float4));
+    L.total = L.p2f_off + align256(n * 4 * sizeof(float));
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: kernel.cu:222-282 + the per-face parts of :32-44
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prep(const float* __restrict__ fv, float* __restrict__ rec,
+                                              float4* __restrict__ box, int n, float r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* f = fv + (size_t)i * 9;
+    float v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = __ldg(f + k);
+    const float x0 = v[0], y0 = v[1], x1 = v[3], y1 = v[4], x2 = v[6], y2 = v[7];
+    float star[9] = {y1 - y2, x2 - x1, x1 * y2 - x2 * y1,  //
+                     y2 - y0, x0 - x2, x2 * y0 - x0 * y2,  //
+                     y0 - y1, x1 - x0, x0 * y1 - x1 * y0};
+    float det = x2 * (y0 - y1) + x0 * (y1 - y2) + x1 * (y2 - y0);
+    // max(det, 1e-10) / min(det, -1e-10) are evaluated in double by the reference and stored as
+    // float; a float select against the rounded constant is bit-identical.
+    det = det > 0 ? fmaxf(det, 1e-10f) : fminf(det, -1e-10f);
+    float out[REC_F];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[R_V + k] = v[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[R_INV + k] = star[k] / det;
+    out[R_SYM + 0] = x0 * x0 + y0 * y0 + 1.f;
+    out[R_SYM + 1] = x0 * x1 + y0 * y1 + 1.f;
+    out[R_SYM + 2] = x0 * x2 + y0 * y2 + 1.f;
+    out[R_SYM + 3] = x1 * x1 + y1 * y1 + 1.f;
+    out[R_SYM + 4] = x1 * x2 + y1 * y2 + 1.f;
+    out[R_SYM + 5] = x2 * x2 + y2 * y2 + 1.f;
+    const float xlo = fminf(fminf(x0, x1), x2) - r, xhi = fmaxf(fmaxf(x0, x1), x2) + r;
+    const float ylo = fminf(fminf(y0, y1), y2) - r, yhi = fmaxf(fmaxf(y0, y1), y2) + r;
+    out[R_BOX + 0] = xlo;
+    out[R_BOX + 1] = xhi;
+    out[R_BOX + 2] = ylo;
+    out[R_BOX + 3] = yhi;
+    uint32_t flags = 0;
+    if ((x1 - x0) * (x2 - x0) + (y1 - y0) * (y2 - y0) < 0) flags = 1;
+    else if ((x2 - x1) * (x0 - x1) + (y2 - y1) * (y0 - y1) < 0) flags = 2;
+    else if ((x0 - x2) * (x1 - x2) + (y0 - y2) * (y1 - y2) < 0) flags = 4;
+    if ((y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0)) flags |= 8;  // kernel.cu:42-44
+    out[R_FLG] = __uint_as_float(flags);
+    out[29] = out[30] = out[31] = 0.f;
+    float4* dst = reinterpret_cast<float4*>(rec + (size_t)i * REC_F);
+#pragma unroll
+    for (int k = 0; k < REC_F / 4; ++k)
+        dst[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+    box[i] = make_float4(xlo, xhi, ylo, yhi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared per-(pixel, face) math
+// ---------------------------------------------------------------------------------------------
+struct Frag {
+    float w0, w1, w2;  // unclipped barycentrics
+    float t0, t1, t2;  // closest-point barycentrics minus w
+    float sign, dx, dy, dis, D;
+};
+
+__device__ __forceinline__ float pixel_coord(int i, int S) {  // kernel.cu:325-326 (double, then float)
+    return (float)((2. * i + 1. - S) / S);
+}
+
+// euclidean signed distance + sigmoid: kernel.cu:62-152, 380-383.  `rc` points at a staged record.
+// Returns false when the pair is culled (outside and farther than the threshold).
+__device__ __forceinline__ bool fragment(const float* __restrict__ rc, float xp, float yp, float thr,
+                                         float sigma, Frag& fr) {
+    const float w0 = rc[R_INV + 0] * xp + rc[R_INV + 1] * yp + rc[R_INV + 2];
+    const float w1 = rc[R_INV + 3] * xp + rc[R_INV + 4] * yp + rc[R_INV + 5];
+    const float w2 = rc[R_INV + 6] * xp + rc[R_INV + 7] * yp + rc[R_INV + 8];
+    fr.w0 = w0; fr.w1 = w1; fr.w2 = w2;
+    const float fx0 = rc[0], fy0 = rc[1], fx1 = rc[3], fy1 = rc[4], fx2 = rc[6], fy2 = rc[7];
+    const float s00 = rc[R_SYM + 0], s01 = rc[R_SYM + 1], s02 = rc[R_SYM + 2];
+    const float s11 = rc[R_SYM + 3], s12 = rc[R_SYM + 4], s22 = rc[R_SYM + 5];
+    float dx, dy, t0, t1, t2;
+    if (w0 > 0 && w1 > 0 && w2 > 0 && w0 < 1 && w1 < 1 && w2 < 1) {
+        float best = 100000000.f;
+        // edge k=0: v0=0,v1=1,v2=2    a = sym[0,:] - sym[1,:]
+        {
+            const float a0 = s00 - s01, a1 = s01 - s11, a2 = s02 - s12;
+            float u0 = (w0 * a0 + w1 * a1 + w2 * a2 - a1) / (a0 - a1);
+            float u1 = 1 - u0;
+            float u2 = 0;
+            u0 -= w0; u1 -= w1; u2 -= w2;
+            const float ex = u0 * fx0 + u1 * fx1 + u2 * fx2;
+            const float ey = u0 * fy0 + u1 * fy1 + u2 * fy2;
+            const float d = ex * ex + ey * ey;
+            dx = 0.f; dy = 0.f; t0 = t1 = t2 = 0.f;
+            if (d < best) { best = d; dx = ex; dy = ey; t0 = u0; t1 = u1; t2 = u2; }
+        }
+        // edge k=1: v0=1,v1=2,v2=0    a = sym[1,:] - sym[2,:]
+        {
+            const float a0 = s01 - s02, a1 = s11 - s12, a2 = s12 - s22;
+            float u1 = (w0 * a0 + w1 * a1 + w2 * a2 - a2) / (a1 - a2);
+            float u2 = 1 - u1;
+            float u0 = 0;
+            u0 -= w0; u1 -= w1; u2 -= w2;
+            const float ex = u0 * fx0 + u1 * fx1 + u2 * fx2;
+            const float ey = u0 * fy0 + u1 * fy1 + u2 * fy2;
+            const float d = ex * ex + ey * ey;
+            if (d < best) { best = d; dx = ex; dy = ey; t0 = u0; t1 = u1; t2 = u2; }
+        }
+        // edge k=2: v0=2,v1=0,v2=1    a = sym[2,:] - sym[0,:]
+        {
+            const float a0 = s02 - s00, a1 = s12 - s01, a2 = s22 - s02;
+            float u2 = (w0 * a0 + w1 * a1 + w2 * a2 - a0) / (a2 - a0);
+            float u0 = 1 - u2;
+            float u1 = 0;
+            u0 -= w0; u1 -= w1; u2 -= w2;
+            const float ex = u0 * fx0 + u1 * fx1 + u2 * fx2;
+            const float ey = u0 * fy0 + u1 * fy1 + u2 * fy2;
+            const float d = ex * ex + ey * ey;
+            if (d < best) { best = d; dx = ex; dy = ey; t0 = u0; t1 = u1; t2 = u2; }
+        }
+        fr.sign = 1.f;
+    } else {
+        const uint32_t flg = __float_as_uint(rc[R_FLG]);
+        int v0 = -1;
+        if (w1 <= 0 && w2 <= 0) {
+            v0 = 0;
+            if ((flg & 1u) && (xp - fx0) * (fx2 - fx0) + (yp - fy0) * (fy2 - fy0) > 0) v0 = 2;
+        } else if (w2 <= 0 && w0 <= 0) {
+            v0 = 1;
+            if ((flg & 2u) && (xp - fx1) * (fx0 - fx1) + (yp - fy1) * (fy0 - fy1) > 0) v0 = 0;
+        } else if (w0 <= 0 && w1 <= 0) {
+            v0 = 2;
+            if ((flg & 4u) && (xp - fx2) * (fx1 - fx2) + (yp - fy2) * (fy1 - fy2) > 0) v0 = 1;
+        } else if (w0 <= 0) v0 = 1;
+        else if (w1 <= 0) v0 = 2;
+        else if (w2 <= 0) v0 = 0;
+        // all w > 0 but some w >= 1 (rounding): undefined in the reference (kernel.cu:128-139 runs
+        // with v0 = -1).  Defined as "corner with the largest barycentric", like oracle B.
+        if (v0 < 0) v0 = w0 >= w1 ? (w0 >= w2 ? 0 : 2) : (w1 >= w2 ? 1 : 2);
+        float u0, u1, u2;
+        if (v0 == 0) {  // v1 = 1, v2 = 2
+            const float a0 = s00 - s01, a1 = s01 - s11, a2 = s02 - s12;
+            u0 = (w0 * a0 + w1 * a1 + w2 * a2 - a1) / (a0 - a1);
+            u1 = 1 - u0;
+            u2 = 0;
+        } else if (v0 == 1) {  // v1 = 2, v2 = 0
+            const float a0 = s01 - s02, a1 = s11 - s12, a2 = s12 - s22;
+            u1 = (w0 * a0 + w1 * a1 + w2 * a2 - a2) / (a1 - a2);
+            u2 = 1 - u1;
+            u0 = 0;
+        } else {  // v0 = 2, v1 = 0, v2 = 1
+            const float a0 = s02 - s00, a1 = s12 - s01, a2 = s22 - s02;
+            u2 = (w0 * a0 + w1 * a1 + w2 * a2 - a0) / (a2 - a0);
+            u0 = 1 - u2;
+            u1 = 0;
+        }
+        // min(max(t, 0.), 1.) in double then float == float clamp (values are only selected)
+        u0 = fminf(fmaxf(u0, 0.f), 1.f) - w0;
+        u1 = fminf(fmaxf(u1, 0.f), 1.f) - w1;
+        u2 = fminf(fmaxf(u2, 0.f), 1.f) - w2;
+        t0 = u0; t1 = u1; t2 = u2;
+        dx = t0 * fx0 + t1 * fx1 + t2 * fx2;
+        dy = t0 * fy0 + t1 * fy1 + t2 * fy2;
+        fr.sign = -1.f;
+    }
+    const float dis = dx * dx + dy * dy;
+    if (fr.sign < 0 && dis >= thr) return false;
+    fr.t0 = t0; fr.t1 = t1; fr.t2 = t2;
+    fr.dx = dx; fr.dy = dy; fr.dis = dis;
+    // 1. / (1. + exp(-sign * dis / sigma)): float exp, double add + divide, float result (:383)
+    const float e = expf(-fr.sign * dis / sigma);
+    fr.D = (float)(1. / (1. + (double)e));
+    return true;
+}
+
+// NaN-aware note: fmaxf/fminf return the non-NaN operand whereas the reference's comparisons
+// propagate differently; inputs with NaN coordinates are outside the supported domain.
+
+__device__ __forceinline__ void clip_bary(float& w0, float& w1, float& w2) {  // kernel.cu:54-59
+    const float hi = (float)(1 - 1e-5), lo = (float)1e-5;
+    w0 = fmaxf(fminf(w0, hi), lo);
+    w1 = fmaxf(fminf(w1, hi), lo);
+    w2 = fmaxf(fminf(w2, hi), lo);
+    const float s = fmaxf(w0 + w1 + w2, lo);
+    w0 /= s; w1 /= s; w2 /= s;
+}
+
+__device__ __forceinline__ float depth_of(const float* __restrict__ rc, float c0, float c1, float c2) {
+    return (float)(1. / (double)(c0 / rc[2] + c1 / rc[5] + c2 / rc[8]));  // kernel.cu:403
+}
+
+__device__ __forceinline__ int texel_index(float c0, float c1, int R) {  // kernel.cu:180-190
+    const int wx = (int)(c0 * R);
+    const int wy = (int)(c1 * R);
+    if ((c0 + c1) * R - wx - wy <= 1) return wy * R + wx;
+    return (R - 1 - wy) * R + (R - 1 - wx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile machinery shared by forward and backward
+// ---------------------------------------------------------------------------------------------
+struct TileSmem {
+    // dynamic shared memory layout (bytes):  [ records NSTAGE*CHUNK*128 | list u16[F_pad] ]
+    float* rec;       // NSTAGE * CHUNK * REC_F floats
+    uint16_t* list;   // ordered face indices touching the tile
+};
+
+// Ordered compaction of the faces whose cull box touches the tile.  Returns the list length
+// (uniform across the CTA).  box: [F] float4 of this image.
+__device__ __forceinline__ int build_tile_list(const float4* __restrict__ box, int F, float tx_first,
+                                               float tx_last, float ty_bot, float ty_top,
+                                               uint16_t* list, int* s_warp_cnt, int* s_total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int total = 0;
+    for (int base = 0; base < F; base += CTA) {
+        const int f = base + tid;
+        bool hit = false;
+        if (f < F) {
+            const float4 bb = __ldg(box + f);
+            hit = !(tx_first > bb.y || tx_last < bb.x || ty_bot > bb.w || ty_top < bb.z);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int off = total;
+#pragma unroll
+        for (int w = 0; w < CTA / 32; ++w) {
+            const int c = s_warp_cnt[w];
+            if (w < warp) off += c;
+            total += c;
+        }
+        if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)f;
+        __syncthreads();
+    }
+    (void)s_total;
+    return total;
+}
+
+// issue the TMA bulk copies of chunk c (records list[c*CHUNK ...]) into stage c % NSTAGE; warp 0 only
+__device__ __forceinline__ void issue_chunk(const float* __restrict__ rec_img, const uint16_t* list, int n,
+                                            int c, float* s_rec, uint64_t* bars) {
+    const int lane = threadIdx.x & 31;
+    const int st = c % NSTAGE;
+    const int begin = c * CHUNK;
+    const int cnt = min(CHUNK, n - begin);
+    if (lane == 0) mbar_arrive_expect_tx(&bars[st], (uint32_t)cnt * REC_F * 4u);
+    __syncwarp();
+    if (lane < cnt) {
+        const int f = list[begin + lane];
+        tma_bulk_g2s(s_rec + ((size_t)st * CHUNK + lane) * REC_F, rec_img + (size_t)f * REC_F,
+                     REC_F * 4u, &bars[st]);
+    }
+}
+
+struct Consts {
+    float thr, sigma, gamma, near_, far_, inv_unused;
+    int F, T2, R, S, IS, aa, double_side;
+};
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int RGB>  // 1 softmax, 0 hard
+__global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ rec_all,
+                                                    const float4* __restrict__ box_all,
+                                                    const float* __restrict__ textures,
+                                                    float* __restrict__ images, float* __restrict__ colors_hi,
+                                                    float* __restrict__ aggrs, float* __restrict__ p2f_acc,
+                                                    Consts K, float eps, float bg0, float bg1, float bg2) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_rec = reinterpret_cast<float*>(smem_raw);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NSTAGE * CHUNK * REC_F * 4);
+    __shared__ uint64_t s_bar[NSTAGE];
+    __shared__ int s_warp_cnt[CTA / 32];
+    __shared__ float s_p2f[CHUNK][3];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int S = K.S, F = K.F;
+    // lane -> pixel: a warp covers a 16x2 strip so the 2x2 pool partners are lanes ^1 and ^16
+    const int px = blockIdx.x * TILE + (lane & 15);
+    const int py = blockIdx.y * TILE + warp * 2 + (lane >> 4);  // image row (0 = top)
+    const bool live = px < S && py < S;
+    const float xp = pixel_coord(px, S);
+    const float yp = pixel_coord(S - 1 - py, S);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_bar[s], 1);
+        fence_mbar_init();
+    }
+    // tile extents in pixel-centre coordinates (monotone in the index, so the test is conservative)
+    const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
+    const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
+    const float tx_first = pixel_coord(blockIdx.x * TILE, S), tx_last = pixel_coord(x_last_i, S);
+    const float ty_top = pixel_coord(S - 1 - blockIdx.y * TILE, S), ty_bot = pixel_coord(S - 1 - y_last_i, S);
+
+    const float4* box = box_all + (size_t)b * F;
+    const float* rec_img = rec_all + (size_t)b * F * REC_F;
+    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_list, s_warp_cnt, nullptr);
+    // (build_tile_list ends with __syncthreads: barrier init + list are visible)
+
+    // pixel state (kernel.cu:335-348)
+    float acc_a = 1.f;  // prod alpha accumulator
+    float ssum = expf(eps / K.gamma);
+    float smax = eps;
+    float c0, c1, c2;
+    if (RGB == 1) { c0 = bg0 * ssum; c1 = bg1 * ssum; c2 = bg2 * ssum; }
+    else { c0 = bg0; c1 = bg1; c2 = bg2; }
+    float zmin = 10000000.f;
+    int fid = -1;
+
+    const int nchunk = (n + CHUNK - 1) / CHUNK;
+    if (warp == 0) {
+        if (nchunk > 0) issue_chunk(rec_img, s_list, n, 0, s_rec, s_bar);
+        if (nchunk > 1) issue_chunk(rec_img, s_list, n, 1, s_rec, s_bar);
+    }
+    const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
+    // torch-1.1 affine_grid (align_corners=True) coordinates of this pixel: linspace(-1, 1, S)
+    const float gstep = 2.f / (float)(S - 1);
+    const float gx = (px * 2 < S) ? (-1.f + gstep * px) : (1.f - gstep * (S - 1 - px));
+    const float gy = (py * 2 < S) ? (-1.f + gstep * py) : (1.f - gstep * (S - 1 - py));
+
+    for (int c = 0; c < nchunk; ++c) {
+        const int st = c % NSTAGE;
+        const int cnt = min(CHUNK, n - c * CHUNK);
+        if (RGB == 1 && tid < CHUNK * 3) (&s_p2f[0][0])[tid] = 0.f;
+        mbar_wait(&s_bar[st], (uint32_t)((c / NSTAGE) & 1));
+        if (RGB == 1) __syncthreads();  // s_p2f zero visible
+        const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
+        for (int j = 0; j < cnt; ++j) {
+            const float* rc = chunk + j * REC_F;
+            const float4 bb = *reinterpret_cast<const float4*>(rc + R_BOX);
+            float a_x = 0.f, a_y = 0.f, a_w = 0.f;
+            bool contrib = false;
+            if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
+                Frag fr;
+                if (fragment(rc, xp, yp, K.thr, K.sigma, fr)) {
+                    acc_a = (float)((double)acc_a * (1. - (double)fr.D));  // kernel.cu:396
+                    float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
+                    clip_bary(k0, k1, k2);
+                    const float zp = depth_of(rc, k0, k1, k2);
+                    if (!(zp < K.near_ || zp > K.far_)) {
+                        const uint32_t flg = __float_as_uint(rc[R_FLG]);
+                        const bool front = (flg & 8u) != 0;
+                        const int f = s_list[c * CHUNK + j];
+                        if (RGB == 0) {
+                            const bool inside = fr.w0 <= 1 && fr.w0 >= 0 && fr.w1 <= 1 && fr.w1 >= 0 &&
+                                                fr.w2 <= 1 && fr.w2 >= 0;
+                            if (zp < zmin && inside && (K.double_side || front)) {
+                                zmin = zp;
+                                fid = f;
+                                const float* tx = tex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                                c0 = __ldg(tx); c1 = __ldg(tx + 1); c2 = __ldg(tx + 2);
+                            }
+                        } else if (front || K.double_side) {
+                            const float zn = (K.far_ - zp) / (K.far_ - K.near_);
+                            float ed = 1.f;
+                            if (zn > smax) { ed = expf((smax - zn) / K.gamma); smax = zn; }
+                            const float ez = expf((zn - smax) / K.gamma);
+                            ssum = ed * ssum + ez * fr.D;
+                            const float a = ez * fr.D;
+                            a_x = a * gx; a_y = a * gy; a_w = a;
+                            contrib = true;
+                            const float* tx = tex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                            c0 = ed * c0 + a * __ldg(tx);
+                            c1 = ed * c1 + a * __ldg(tx + 1);
+                            c2 = ed * c2 + a * __ldg(tx + 2);
+                        }
+                    }
+                }
+            }
+            if (RGB == 1) {
+                // p2f: warp-shuffle reduction, one shared atomic per warp (replaces the 4 global
+                // atomics per (pixel, face) of kernel.cu:427-430)
+                if (__any_sync(0xffffffffu, contrib)) {
+                    a_x = warp_sum(a_x); a_y = warp_sum(a_y); a_w = warp_sum(a_w);
+                    if (lane == 0) {
+                        atomicAdd(&s_p2f[j][0], a_x);
+                        atomicAdd(&s_p2f[j][1], a_y);
+                        atomicAdd(&s_p2f[j][2], a_w);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with stage st (and s_p2f is complete)
+        if (RGB == 1 && p2f_acc != nullptr && tid < cnt * 3) {
+            const int j = tid / 3, k = tid - j * 3;
+            const float v = s_p2f[j][k];
+            if (v != 0.f) atomicAdd(p2f_acc + ((size_t)b * F + s_list[c * CHUNK + j]) * 4 + k, v);
+        }
+        if (warp == 0 && c + NSTAGE < nchunk) issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec, s_bar);
+        if (RGB == 1) __syncthreads();  // s_p2f flushed before the next chunk zeroes it
+    }
+
+    // finalise (kernel.cu:443-475)
+    const float alpha = (float)(1. - (double)acc_a);
+    float o0, o1, o2, g0, g1;
+    if (RGB == 0) {
+        o0 = c0; o1 = c1; o2 = c2;  // background kept when no face won (c* still bg)
+        g0 = zmin; g1 = (float)fid;
+    } else {
+        o0 = c0 / ssum; o1 = c1 / ssum; o2 = c2 / ssum;
+        g0 = ssum; g1 = smax;
+    }
+    const size_t np = (size_t)S * S;
+    if (live) {
+        const size_t p = (size_t)py * S + px;
+        aggrs[((size_t)b * 2 + 0) * np + p] = g0;
+        aggrs[((size_t)b * 2 + 1) * np + p] = g1;
+        if (colors_hi != nullptr) {
+            colors_hi[((size_t)b * 4 + 0) * np + p] = o0;
+            colors_hi[((size_t)b * 4 + 1) * np + p] = o1;
+            colors_hi[((size_t)b * 4 + 2) * np + p] = o2;
+            colors_hi[((size_t)b * 4 + 3) * np + p] = alpha;
+        }
+    }
+    if (K.aa) {
+        // avg_pool2d(2,2): ((a00 + a01) + a10) + a11, then /4 (rasterizer.py:52-53)
+        float v[4] = {o0, o1, o2, alpha};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a01 = __shfl_xor_sync(0xffffffffu, v[k], 1);
+            const float a10 = __shfl_xor_sync(0xffffffffu, v[k], 16);
+            const float a11 = __shfl_xor_sync(0xffffffffu, v[k], 17);
+            v[k] = (((v[k] + a01) + a10) + a11) * 0.25f;  // meaningful on the (even x, even y) lane
+        }
+        if (live && (lane & 1) == 0 && (lane & 16) == 0) {
+            const int IS = K.IS;
+            const size_t q = (size_t)(py >> 1) * IS + (px >> 1);
+            const size_t nq = (size_t)IS * IS;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * nq + q] = v[k];
+        }
+    } else if (live && images != colors_hi) {
+        const size_t p = (size_t)py * S + px;
+        images[((size_t)b * 4 + 0) * np + p] = o0;
+        images[((size_t)b * 4 + 1) * np + p] = o1;
+        images[((size_t)b * 4 + 2) * np + p] = o2;
+        images[((size_t)b * 4 + 3) * np + p] = alpha;
+    }
+}
+
+__global__ void k_p2f_finalize(const float* __restrict__ acc, float* __restrict__ p2f, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = reinterpret_cast<const float4*>(acc)[i];
+    const float d = fmaxf(a.z, 1e-12f);  // soft_rasterize.py:73 clamp_min(1e-12)
+    reinterpret_cast<float2*>(p2f)[i] = make_float2(a.x / d, a.y / d);
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+template <int RGB, bool TEXGRAD>
+__global__ void __launch_bounds__(CTA) k_raster_bwd(const float* __restrict__ rec_all,
+                                                    const float4* __restrict__ box_all,
+                                                    const float* __restrict__ textures,
+                                                    const float* __restrict__ colors_hi,
+                                                    const float* __restrict__ aggrs,
+                                                    const float* __restrict__ grad_images,
+                                                    float* __restrict__ grad_faces, float* __restrict__ grad_tex,
+                                                    Consts K) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_rec = reinterpret_cast<float*>(smem_raw);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NSTAGE * CHUNK * REC_F * 4);
+    __shared__ uint64_t s_bar[NSTAGE];
+    __shared__ int s_warp_cnt[CTA / 32];
+    __shared__ float s_g[CHUNK][9];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int S = K.S, F = K.F;
+    const int px = blockIdx.x * TILE + (lane & 15);
+    const int py = blockIdx.y * TILE + warp * 2 + (lane >> 4);
+    const bool live = px < S && py < S;
+    const float xp = pixel_coord(px, S);
+    const float yp = pixel_coord(S - 1 - py, S);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_bar[s], 1);
+        fence_mbar_init();
+    }
+    const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
+    const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
+    const float tx_first = pixel_coord(blockIdx.x * TILE, S), tx_last = pixel_coord(x_last_i, S);
+    const float ty_top = pixel_coord(S - 1 - blockIdx.y * TILE, S), ty_bot = pixel_coord(S - 1 - y_last_i, S);
+    const float4* box = box_all + (size_t)b * F;
+    const float* rec_img = rec_all + (size_t)b * F * REC_F;
+    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_list, s_warp_cnt, nullptr);
+    if (n == 0) return;  // uniform
+
+    const int nchunk = (n + CHUNK - 1) / CHUNK;
+    if (warp == 0) {
+        issue_chunk(rec_img, s_list, n, 0, s_rec, s_bar);
+        if (nchunk > 1) issue_chunk(rec_img, s_list, n, 1, s_rec, s_bar);
+    }
+
+    // per-pixel inputs
+    const size_t np = (size_t)S * S;
+    float g0 = 0, g1 = 0, g2 = 0, g3 = 0, C0 = 0, C1 = 0, C2 = 0, C3 = 0, ssum = 1, smax = 0;
+    if (live) {
+        const size_t p = (size_t)py * S + px;
+        if (K.aa) {  // avg_pool2d backward: g / 4
+            const size_t nq = (size_t)K.IS * K.IS;
+            const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
+            g0 = __ldg(grad_images + ((size_t)b * 4 + 0) * nq + q) * 0.25f;
+            g1 = __ldg(grad_images + ((size_t)b * 4 + 1) * nq + q) * 0.25f;
+            g2 = __ldg(grad_images + ((size_t)b * 4 + 2) * nq + q) * 0.25f;
+            g3 = __ldg(grad_images + ((size_t)b * 4 + 3) * nq + q) * 0.25f;
+        } else {
+            g0 = __ldg(grad_images + ((size_t)b * 4 + 0) * np + p);
+            g1 = __ldg(grad_images + ((size_t)b * 4 + 1) * np + p);
+            g2 = __ldg(grad_images + ((size_t)b * 4 + 2) * np + p);
+            g3 = __ldg(grad_images + ((size_t)b * 4 + 3) * np + p);
+        }
+        C0 = __ldg(colors_hi + ((size_t)b * 4 + 0) * np + p);
+        C1 = __ldg(colors_hi + ((size_t)b * 4 + 1) * np + p);
+        C2 = __ldg(colors_hi + ((size_t)b * 4 + 2) * np + p);
+        C3 = __ldg(colors_hi + ((size_t)b * 4 + 3) * np + p);
+        ssum = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
+        smax = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
+    }
+    const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
+    float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * F * K.T2 * 3 : nullptr;
+
+    for (int c = 0; c < nchunk; ++c) {
+        const int st = c % NSTAGE;
+        const int cnt = min(CHUNK, n - c * CHUNK);
+        for (int i = tid; i < CHUNK * 9; i += CTA) (&s_g[0][0])[i] = 0.f;
+        mbar_wait(&s_bar[st], (uint32_t)((c / NSTAGE) & 1));
+        __syncthreads();
+        const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
+        for (int j = 0; j < cnt; ++j) {
+            const float* rc = chunk + j * REC_F;
+            const float4 bb = *reinterpret_cast<const float4*>(rc + R_BOX);
+            float gv[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) gv[k] = 0.f;
+            bool contrib = false;
+            if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
+                Frag fr;
+                if (fragment(rc, xp, yp, K.thr, K.sigma, fr)) {
+                    // alpha (prod): kernel.cu:577-585
+                    float Cxy = (float)((double)g3 * ((double)(1 - C3) / fmax((double)(1 - fr.D), 1e-6)));
+                    float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
+                    clip_bary(k0, k1, k2);
+                    const float zp = depth_of(rc, k0, k1, k2);
+                    if (!(zp < K.near_ || zp > K.far_)) {  // :592 drops the alpha gradient as well
+                        contrib = true;
+                        const uint32_t flg = __float_as_uint(rc[R_FLG]);
+                        const bool front = (flg & 8u) != 0;
+                        const int f = s_list[c * CHUNK + j];
+                        float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
+                        if (RGB == 0) {
+                            if ((float)f == smax) {  // aggrs[1] = winning face id (:596)
+                                if (TEXGRAD) {
+                                    float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                                    atomicAdd(gt + 0, g0);
+                                    atomicAdd(gt + 1, g1);
+                                    atomicAdd(gt + 2, g2);
+                                }
+                            }
+                        } else if (front || K.double_side) {
+                            const float zn = (K.far_ - zp) / (K.far_ - K.near_);
+                            const float s = fr.D * expf((zn - smax) / K.gamma) / ssum;  // :608
+                            const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                            if (TEXGRAD) {
+                                atomicAdd(gtex_img + to + 0, s * g0);
+                                atomicAdd(gtex_img + to + 1, s * g1);
+                                atomicAdd(gtex_img + to + 2, s * g2);
+                            }
+                            float Crgb = 0.f;
+                            Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
+                            Crgb += g1 * (__ldg(tex_img + to + 1) - C1);
+                            Crgb += g2 * (__ldg(tex_img + to + 2) - C2);
+                            Crgb *= s;
+                            Cxy += Crgb / fr.D;
+                            const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
+                            gz0 = Cz * k0 / rc[2] / rc[2];
+                            gz1 = Cz * k1 / rc[5] / rc[5];
+                            gz2 = Cz * k2 / rc[8] / rc[8];
+                        }
+                        Cxy *= fr.D * (1 - fr.D) / K.sigma;  // :632
+                        const float q = 2 * fr.sign * Cxy;      // :640
+                        gv[0] = q * (fr.t0 + fr.w0) * fr.dx;
+                        gv[1] = q * (fr.t0 + fr.w0) * fr.dy;
+                        gv[2] = gz0;
+                        gv[3] = q * (fr.t1 + fr.w1) * fr.dx;
+                        gv[4] = q * (fr.t1 + fr.w1) * fr.dy;
+                        gv[5] = gz1;
+                        gv[6] = q * (fr.t2 + fr.w2) * fr.dx;
+                        gv[7] = q * (fr.t2 + fr.w2) * fr.dy;
+                        gv[8] = gz2;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, contrib)) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gv[k] = warp_sum(gv[k]);
+                if (lane < 9) {
+                    float v = gv[0];
+#pragma unroll
+                    for (int k = 1; k < 9; ++k) v = (lane == k) ? gv[k] : v;
+                    atomicAdd(&s_g[j][lane], v);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < cnt * 9; i += CTA) {
+            const int j = i / 9, k = i - j * 9;
+            const float v = s_g[j][k];
+            if (v != 0.f) atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
+        }
+        if (warp == 0 && c + NSTAGE < nchunk) issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec, s_bar);
+        __syncthreads();
+    }
+}
+
+}  // namespace umr
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace umr;
+
+extern "C" size_t umr_raster_workspace_bytes(int32_t B, int32_t F) {
+    if (B <= 0 || F <= 0) return 0;
+    return ws_layout(B, F).total;
+}
+
+static int check_params(const UmrRasterParams* p) {
+    if (!p) return UMR_ERR_BAD_ARG;
+    if (p->batch_size <= 0 || p->num_faces <= 0 || p->texture_size <= 0 || p->image_size <= 0)
+        return UMR_ERR_BAD_ARG;
+    if (p->num_faces > 65535 || p->batch_size > 65535) return UMR_ERR_TOO_LARGE;
+    if (p->func_id_dist != UMR_DIST_EUCLIDEAN || p->func_id_alpha != UMR_ALPHA_PROD ||
+        p->texture_sample_type != UMR_TEX_SURFACE)
+        return UMR_ERR_UNSUPPORTED;
+    if (p->func_id_rgb != UMR_RGB_HARD && p->func_id_rgb != UMR_RGB_SOFTMAX) return UMR_ERR_UNSUPPORTED;
+    return UMR_OK;
+}
+
+static Consts make_consts(const UmrRasterParams* p) {
+    Consts K;
+    K.thr = p->dist_eps * p->sigma_val;  // kernel.cu:333 (float * float)
+    K.sigma = p->sigma_val;
+    K.gamma = p->gamma_val;
+    K.near_ = p->near_plane;
+    K.far_ = p->far_plane;
+    K.inv_unused = 0.f;
+    K.F = p->num_faces;
+    K.T2 = p->texture_size;
+    K.R = (int)sqrt((double)p->texture_size);  // kernel.cu:685
+    K.IS = p->image_size;
+    K.aa = p->anti_aliasing ? 1 : 0;
+    K.S = p->image_size * (K.aa ? 2 : 1);
+    K.double_side = p->double_side ? 1 : 0;
+    return K;
+}
+
+static size_t raster_dyn_smem(int F) {
+    return (size_t)NSTAGE * CHUNK * REC_F * 4 + (((size_t)F * 2 + 15) & ~(size_t)15);
+}
+
+extern "C" int umr_raster_forward(const float* face_vertices, const float* textures, float* images,
+                                  float* soft_colors, float* aggrs_info, float* p2f_info,
+                                  const UmrRasterParams* p, void* workspace, void* stream_) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!face_vertices || !textures || !images || !aggrs_info || !workspace) return UMR_ERR_BAD_ARG;
+    if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int B = p->batch_size, F = p->num_faces;
+    const Consts K = make_consts(p);
+    if (!K.aa && soft_colors == nullptr) soft_colors = images;
+    const WorkspaceLayout L = ws_layout(B, F);
+    char* ws = (char*)workspace;
+    float* rec = (float*)(ws + L.rec_off);
+    float4* box = (float4*)(ws + L.box_off);
+    float* p2f_acc = (float*)(ws + L.p2f_off);
+    const int n = B * F;
+    const float r = sqrtf(K.thr);  // kernel.cu:355 sqrt(threshold) in float
+    k_prep<<<(n + 255) / 256, 256, 0, stream>>>(face_vertices, rec, box, n, r);
+    const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
+    const bool want_p2f = p2f_info != nullptr;
+    if (want_p2f && softmax) {
+        cudaError_t e = cudaMemsetAsync(p2f_acc, 0, (size_t)n * 4 * sizeof(float), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
+    const size_t smem = raster_dyn_smem(F);
+    if (softmax) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(k_raster_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_raster_fwd<1><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
+                                                     want_p2f ? p2f_acc : nullptr, K, p->eps,
+                                                     p->background_color[0], p->background_color[1],
+                                                     p->background_color[2]);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(k_raster_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_raster_fwd<0><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
+                                                     nullptr, K, p->eps, p->background_color[0],
+                                                     p->background_color[1], p->background_color[2]);
+    }
+    if (want_p2f) {
+        if (softmax) {
+            k_p2f_finalize<<<(n + 255) / 256, 256, 0, stream>>>(p2f_acc, p2f_info, (size_t)n);
+        } else {  // hard mode never accumulates p2f (kernel.cu:417-431 is softmax-only) -> zeros
+            cudaError_t e = cudaMemsetAsync(p2f_info, 0, (size_t)n * 2 * sizeof(float), stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int umr_raster_backward(const float* face_vertices, const float* textures,
+                                   const float* soft_colors, const float* aggrs_info,
+                                   const float* grad_images, float* grad_faces, float* grad_textures,
+                                   const UmrRasterParams* p, void* workspace, void* stream_) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !grad_images || !grad_faces ||
+        !workspace)
+        return UMR_ERR_BAD_ARG;
+    if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int B = p->batch_size, F = p->num_faces;
+    const Consts K = make_consts(p);
+    const WorkspaceLayout L = ws_layout(B, F);
+    char* ws = (char*)workspace;
+    float* rec = (float*)(ws + L.rec_off);
+    float4* box = (float4*)(ws + L.box_off);
+    const int n = B * F;
+    const float r = sqrtf(K.thr);
+    // the workspace is scratch (another render may have used it since forward): rebuild the records
+    k_prep<<<(n + 255) / 256, 256, 0, stream>>>(face_vertices, rec, box, n, r);
+    cudaError_t e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
+    if (e != cudaSuccess) return (int)e;
+    if (grad_textures) {
+        e = cudaMemsetAsync(grad_textures, 0, (size_t)n * p->texture_size * 3 * sizeof(float), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
+    const size_t smem = raster_dyn_smem(F);
+    const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
+#define UMR_LAUNCH_BWD(RGBM, TG)                                                                        \
+    do {                                                                                                \
+        if (smem > 48 * 1024)                                                                           \
+            cudaFuncSetAttribute(k_raster_bwd<RGBM, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 (int)smem);                                                            \
+        k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+                                                            grad_images, grad_faces, grad_textures, K); \
+    } while (0)
+    if (softmax) {
+        if (grad_textures) UMR_LAUNCH_BWD(1, true); else UMR_LAUNCH_BWD(1, false);
+    } else {
+        if (grad_textures) UMR_LAUNCH_BWD(0, true); else UMR_LAUNCH_BWD(0, false);
+    }
+#undef UMR_LAUNCH_BWD
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,121 @@
+"""torch.autograd binding of the sm_100a soft rasteriser (C ABI: include/umr_b200.h).
+
+Host-side mirror of the reference's autograd Function
+`external/SoftRas/soft_renderer/functional/soft_rasterize.py:9-125` -- same arguments, same
+returned triple -- except that everything the reference did on the host around its kernels is
+fused into ours: no CPU-side buffer fills / H2D copies (soft_rasterize.py:47-62), no `grid`
+tensor, in-kernel p2f normalisation (:73) and, optionally, the 2x2 anti-aliasing average pool of
+`rasterizer.py:52-53` (`anti_aliasing=True`).
+
+There is NO CPU path: CPU tensors raise (the reference intends the same, soft_rasterize.py:117-118).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+FUNC_DIST = {"hard": 0, "barycentric": 1, "euclidean": 2}
+FUNC_RGB = {"hard": 0, "softmax": 1}
+FUNC_ALPHA = {"hard": 0, "sum": 1, "prod": 2}
+FUNC_SAMPLE = {"surface": 0, "vertex": 1}
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def make_params(B, F, T2, image_size, anti_aliasing, background_color, near, far, fill_back, eps,
+                sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, texture_type):
+    p = _lib.UmrRasterParams()
+    p.batch_size, p.num_faces, p.texture_size = B, F, T2
+    p.image_size, p.anti_aliasing = int(image_size), 1 if anti_aliasing else 0
+    p.near_plane, p.far_plane, p.eps = float(near), float(far), float(eps)
+    p.sigma_val, p.gamma_val = float(sigma_val), float(gamma_val)
+    p.dist_eps = float(math.log(1.0 / dist_eps - 1.0))  # soft_rasterize.py:35
+    p.func_id_dist = FUNC_DIST[dist_func]
+    p.func_id_rgb = FUNC_RGB[aggr_func_rgb]
+    p.func_id_alpha = FUNC_ALPHA[aggr_func_alpha]
+    p.texture_sample_type = FUNC_SAMPLE[texture_type]
+    p.double_side = 1 if fill_back else 0
+    for k in range(3):
+        p.background_color[k] = float(background_color[k])
+    return p
+
+
+class SoftRasterizeFunction(torch.autograd.Function):
+    """forward(face_vertices[B,F,3,3|9], textures[B,F,T2,3], ...) ->
+    (images[B,4,is,is], p2f_info[B,F,2], aggrs_info[B,2,S,S]),  S = is * (2 if anti_aliasing else 1)."""
+
+    @staticmethod
+    def forward(ctx, face_vertices, textures, image_size=256, background_color=(0, 0, 0), near=1,
+                far=100, fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean",
+                dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax", aggr_func_alpha="prod",
+                texture_type="surface", anti_aliasing=False):
+        if not face_vertices.is_cuda or not textures.is_cuda:
+            raise TypeError("Rasterize module supports only cuda Tensors")  # soft_rasterize.py:117-118
+        lib = _lib.load()
+        dev = face_vertices.device
+        B, F = face_vertices.shape[:2]
+        fv = face_vertices.detach().reshape(B, F, 9).contiguous().float()
+        tex = textures.detach().contiguous().float()
+        T2 = tex.shape[2]
+        S = int(image_size) * (2 if anti_aliasing else 1)
+        params = make_params(B, F, T2, image_size, anti_aliasing, background_color, near, far, fill_back,
+                             eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb,
+                             aggr_func_alpha, texture_type)
+        need_bwd = face_vertices.requires_grad or textures.requires_grad
+        with torch.cuda.device(dev):
+            images = torch.empty(B, 4, image_size, image_size, device=dev, dtype=torch.float32)
+            if anti_aliasing:
+                colors_hi = torch.empty(B, 4, S, S, device=dev, dtype=torch.float32) if need_bwd else None
+            else:
+                colors_hi = images
+            aggrs = torch.empty(B, 2, S, S, device=dev, dtype=torch.float32)
+            p2f = torch.empty(B, F, 2, device=dev, dtype=torch.float32)
+            ws = torch.empty(lib.umr_raster_workspace_bytes(B, F), device=dev, dtype=torch.uint8)
+            rc = lib.umr_raster_forward(_ptr(fv), _ptr(tex), _ptr(images),
+                                        _ptr(colors_hi) if anti_aliasing else _ptr(None),
+                                        _ptr(aggrs), _ptr(p2f), ctypes.byref(params), _ptr(ws),
+                                        _stream_ptr(dev))
+        _lib.check(rc, "umr_raster_forward")
+        ctx.params = params
+        ctx.in_shape = tuple(face_vertices.shape)
+        ctx.tex_needs_grad = textures.requires_grad
+        if need_bwd:
+            ctx.save_for_backward(fv, tex, colors_hi, aggrs)
+        ctx.mark_non_differentiable(p2f, aggrs)
+        return images, p2f, aggrs
+
+    @staticmethod
+    def backward(ctx, grad_images, grad_p2f=None, grad_aggrs=None):
+        lib = _lib.load()
+        fv, tex, colors_hi, aggrs = ctx.saved_tensors
+        dev = fv.device
+        B, F = fv.shape[:2]
+        g = grad_images.contiguous().float()
+        with torch.cuda.device(dev):
+            grad_faces = torch.empty_like(fv)
+            grad_tex = torch.empty_like(tex) if ctx.tex_needs_grad else None
+            ws = torch.empty(lib.umr_raster_workspace_bytes(B, F), device=dev, dtype=torch.uint8)
+            rc = lib.umr_raster_backward(_ptr(fv), _ptr(tex), _ptr(colors_hi), _ptr(aggrs), _ptr(g),
+                                         _ptr(grad_faces), _ptr(grad_tex), ctypes.byref(ctx.params),
+                                         _ptr(ws), _stream_ptr(dev))
+        _lib.check(rc, "umr_raster_backward")
+        return (grad_faces.view(ctx.in_shape), grad_tex) + (None,) * 14
+
+
+def soft_rasterize(face_vertices, textures, image_size=256, background_color=(0, 0, 0), near=1, far=100,
+                   fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4,
+                   gamma_val=1e-4, aggr_func_rgb="softmax", aggr_func_alpha="prod", texture_type="surface",
+                   anti_aliasing=False):
+    """Drop-in for `soft_renderer.functional.soft_rasterize` (soft_rasterize.py:111-125), plus the
+    optional fused `anti_aliasing` pool (then `image_size` is the OUTPUT size and the raster runs at 2x)."""
+    return SoftRasterizeFunction.apply(face_vertices, textures, image_size, background_color, near, far,
+                                       fill_back, eps, sigma_val, dist_func, dist_eps, gamma_val,
+                                       aggr_func_rgb, aggr_func_alpha, texture_type, anti_aliasing)
