@@ -1,0 +1,190 @@
+"""torch.autograd bindings of the geometric-loss kernels (C ABI: include/umr_b200.h).
+
+CUDA only: there is no CPU fallback (the CPU oracles live in oracle/ and are test infrastructure).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .raster import _ptr, _stream_ptr
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise TypeError("umr_b200 ops support only cuda Tensors")
+
+
+# -------------------------------------------------------------------------------------------------
+# bilinear texture-flow sampler
+# -------------------------------------------------------------------------------------------------
+class BilinearSampleFunction(torch.autograd.Function):
+    """images [B,C,H,W], flow [B,N,2] -> out [B,N,C]; bilinear, zeros padding, align_corners=True
+    (the torch-1.1 semantics the reference was written for: geom_utils.py:55, loss_utils.py:64)."""
+
+    @staticmethod
+    def forward(ctx, images, flow):
+        _need_cuda(images, flow)
+        lib = _lib.load()
+        img = images.detach().contiguous().float()
+        fl = flow.detach().contiguous().float()
+        B, C, H, W = img.shape
+        N = fl.shape[1]
+        with torch.cuda.device(img.device):
+            out = torch.empty(B, N, C, device=img.device, dtype=torch.float32)
+            rc = lib.umr_bilinear_sample_forward(_ptr(img), _ptr(fl), _ptr(out), B, C, H, W, N,
+                                                 _stream_ptr(img.device))
+        _lib.check(rc, "umr_bilinear_sample_forward")
+        ctx.save_for_backward(img, fl)
+        ctx.img_grad = images.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        img, fl = ctx.saved_tensors
+        B, C, H, W = img.shape
+        N = fl.shape[1]
+        g = grad_out.contiguous().float()
+        with torch.cuda.device(img.device):
+            gflow = torch.empty_like(fl)
+            gimg = torch.empty_like(img) if ctx.img_grad else None
+            rc = lib.umr_bilinear_sample_backward(_ptr(img), _ptr(fl), _ptr(g), _ptr(gflow), _ptr(gimg),
+                                                  B, C, H, W, N, _stream_ptr(img.device))
+        _lib.check(rc, "umr_bilinear_sample_backward")
+        return gimg, gflow
+
+
+def bilinear_sample(images, flow):
+    return BilinearSampleFunction.apply(images, flow)
+
+
+# -------------------------------------------------------------------------------------------------
+# silhouette IoU
+# -------------------------------------------------------------------------------------------------
+class NegIouFunction(torch.autograd.Function):
+    """predict/target [B, ...] -> per-image loss [B] = 1 - sum(p*t) / (sum(p+t-p*t) + 1e-6)."""
+
+    @staticmethod
+    def forward(ctx, predict, target):
+        _need_cuda(predict, target)
+        lib = _lib.load()
+        B = predict.shape[0]
+        p = predict.detach().contiguous().float().view(B, -1)
+        t = target.detach().contiguous().float().view(B, -1)
+        N = p.shape[1]
+        with torch.cuda.device(p.device):
+            inter = torch.empty(B, device=p.device, dtype=torch.float32)
+            uni = torch.empty_like(inter)
+            loss = torch.empty_like(inter)
+            rc = lib.umr_iou_forward(_ptr(p), _ptr(t), _ptr(inter), _ptr(uni), _ptr(loss), B, N,
+                                     _stream_ptr(p.device))
+        _lib.check(rc, "umr_iou_forward")
+        ctx.save_for_backward(t, inter, uni)
+        ctx.shape = tuple(predict.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        t, inter, uni = ctx.saved_tensors
+        B, N = t.shape
+        g = grad_loss.contiguous().float()
+        with torch.cuda.device(t.device):
+            gp = torch.empty_like(t)
+            rc = lib.umr_iou_backward(_ptr(t), _ptr(inter), _ptr(uni), _ptr(g), _ptr(gp), B, N,
+                                      _stream_ptr(t.device))
+        _lib.check(rc, "umr_iou_backward")
+        return gp.view(ctx.shape), None
+
+
+def neg_iou_per_image(predict, target):
+    return NegIouFunction.apply(predict, target)
+
+
+# -------------------------------------------------------------------------------------------------
+# chamfer
+# -------------------------------------------------------------------------------------------------
+class ChamferFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _need_cuda(a, b)
+        lib = _lib.load()
+        x = a.detach().contiguous().float()
+        y = b.detach().contiguous().float()
+        B, N, D = x.shape
+        M = y.shape[1]
+        with torch.cuda.device(x.device):
+            d_ab = torch.empty(B, N, device=x.device, dtype=torch.float32)
+            d_ba = torch.empty(B, M, device=x.device, dtype=torch.float32)
+            i_ab = torch.empty(B, N, device=x.device, dtype=torch.int32)
+            i_ba = torch.empty(B, M, device=x.device, dtype=torch.int32)
+            rc = lib.umr_chamfer_forward(_ptr(x), _ptr(y), _ptr(d_ab), _ptr(d_ba), _ptr(i_ab), _ptr(i_ba),
+                                         B, N, M, D, _stream_ptr(x.device))
+        _lib.check(rc, "umr_chamfer_forward")
+        ctx.save_for_backward(x, y, i_ab, i_ba)
+        ctx.mark_non_differentiable(i_ab, i_ba)
+        return d_ab, d_ba, i_ab, i_ba
+
+    @staticmethod
+    def backward(ctx, g_ab, g_ba, _1=None, _2=None):
+        lib = _lib.load()
+        x, y, i_ab, i_ba = ctx.saved_tensors
+        B, N, D = x.shape
+        M = y.shape[1]
+        g1 = g_ab.contiguous().float() if g_ab is not None else None
+        g2 = g_ba.contiguous().float() if g_ba is not None else None
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x)
+            gy = torch.empty_like(y)
+            rc = lib.umr_chamfer_backward(_ptr(x), _ptr(y), _ptr(i_ab), _ptr(i_ba), _ptr(g1), _ptr(g2),
+                                          _ptr(gx), _ptr(gy), B, N, M, D, _stream_ptr(x.device))
+        _lib.check(rc, "umr_chamfer_backward")
+        return gx, gy
+
+
+def dist_chamfer(a, b):
+    return ChamferFunction.apply(a, b)
+
+
+# -------------------------------------------------------------------------------------------------
+# texture cycle
+# -------------------------------------------------------------------------------------------------
+class TexCycleFunction(torch.autograd.Function):
+    """flow [B,F,T2,2], prob [B,F,2], face_ids [B,P] (float plane, -1 = background) -> scalar loss."""
+
+    @staticmethod
+    def forward(ctx, flow, prob, face_ids):
+        _need_cuda(flow, prob, face_ids)
+        lib = _lib.load()
+        fl = flow.detach().contiguous().float()
+        pr = prob.detach().contiguous().float()
+        ids = face_ids.detach().contiguous().float()
+        B, F, T2 = fl.shape[0], fl.shape[1], fl.shape[2]
+        P = ids.shape[1]
+        with torch.cuda.device(fl.device):
+            vis = torch.empty(B, F, device=fl.device, dtype=torch.uint8)
+            loss = torch.empty(1, device=fl.device, dtype=torch.float32)
+            rc = lib.umr_texcycle_forward(_ptr(fl), _ptr(pr), _ptr(ids), _ptr(vis), _ptr(loss), B, F, T2, P,
+                                          _stream_ptr(fl.device))
+        _lib.check(rc, "umr_texcycle_forward")
+        ctx.save_for_backward(fl, pr, vis)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        fl, pr, vis = ctx.saved_tensors
+        B, F, T2 = fl.shape[0], fl.shape[1], fl.shape[2]
+        g = grad_loss.contiguous().float().view(1)
+        with torch.cuda.device(fl.device):
+            gflow = torch.empty_like(fl)
+            rc = lib.umr_texcycle_backward(_ptr(fl), _ptr(pr), _ptr(vis), _ptr(g), _ptr(gflow), B, F, T2,
+                                           _stream_ptr(fl.device))
+        _lib.check(rc, "umr_texcycle_backward")
+        return gflow, None, None
+
+
+def tex_cycle(flow, prob, face_ids):
+    return TexCycleFunction.apply(flow, prob, face_ids)

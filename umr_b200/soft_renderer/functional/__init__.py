@@ -1,0 +1,4 @@
+"""Functional layer of the drop-in package (reference: SoftRas/functional/__init__.py)."""
+from .geometry import face_vertices, look_at, orthogonal, perspective
+from .lights import ambient_lighting, directional_lighting
+from .soft_rasterize import soft_rasterize

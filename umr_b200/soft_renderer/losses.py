@@ -1,0 +1,77 @@
+"""Mesh regularisers UMR takes from SoftRas (reference: SoftRas/losses.py:6-114;
+call sites experiments/train_s2.py:138-139).  Pure torch -- tiny per-step costs."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+class LaplacianLoss(nn.Module):
+    """|L x|^2 with the row-normalised graph Laplacian of the template (losses.py:6-37)."""
+
+    def __init__(self, vertex, faces, average=False):
+        super().__init__()
+        self.nv = vertex.size(0)
+        self.nf = faces.size(0)
+        self.average = average
+        f = faces.detach().cpu().numpy().astype(np.int64)
+        lap = np.zeros((self.nv, self.nv), dtype=np.float32)
+        for a, b in ((0, 1), (1, 2), (2, 0)):
+            lap[f[:, a], f[:, b]] = -1
+            lap[f[:, b], f[:, a]] = -1
+        idx = np.arange(self.nv)
+        lap[idx, idx] = -lap.sum(1)
+        lap = lap / lap[idx, idx][:, None]
+        self.register_buffer("laplacian", torch.from_numpy(lap))
+
+    def forward(self, x):
+        batch_size = x.size(0)
+        x = torch.matmul(self.laplacian, x)
+        x = x.pow(2).sum(tuple(range(1, x.dim())))
+        return x.sum() / batch_size if self.average else x
+
+
+class FlattenLoss(nn.Module):
+    """sum over edges of (cos(dihedral) + 1)^2 (losses.py:39-114).  The edge table (v0, v1 = edge,
+    v2 / v3 = the opposite corners of its two triangles) is built with a dictionary instead of the
+    reference's O(E*F) scan; the loss is symmetric in v2 <-> v3 so the result is the same."""
+
+    def __init__(self, faces, average=False):
+        super().__init__()
+        self.nf = faces.size(0)
+        self.average = average
+        f = faces.detach().cpu().numpy().astype(np.int64)
+        opp = {}
+        for tri in f:
+            for k in range(3):
+                a, b, c = int(tri[k]), int(tri[(k + 1) % 3]), int(tri[(k + 2) % 3])
+                opp.setdefault((min(a, b), max(a, b)), []).append(c)
+        edges = sorted(e for e, o in opp.items() if len(o) >= 2)
+        v0 = [e[0] for e in edges]
+        v1 = [e[1] for e in edges]
+        v2 = [opp[e][0] for e in edges]
+        v3 = [opp[e][1] for e in edges]
+        for name, v in (("v0s", v0), ("v1s", v1), ("v2s", v2), ("v3s", v3)):
+            self.register_buffer(name, torch.tensor(v, dtype=torch.long))
+
+    @staticmethod
+    def _perp(a, b, eps):
+        """Length-scaled component of b perpendicular to a, and its length estimate."""
+        al2 = a.pow(2).sum(-1)
+        bl2 = b.pow(2).sum(-1)
+        al1 = (al2 + eps).sqrt()
+        bl1 = (bl2 + eps).sqrt()
+        ab = (a * b).sum(-1)
+        cos = ab / (al1 * bl1 + eps)
+        sin = (1 - cos.pow(2) + eps).sqrt()
+        c = a * (ab / (al2 + eps))[:, :, None]
+        return b - c, bl1 * sin
+
+    def forward(self, vertices, eps=1e-6):
+        batch_size = vertices.size(0)
+        p0, p1 = vertices[:, self.v0s, :], vertices[:, self.v1s, :]
+        p2, p3 = vertices[:, self.v2s, :], vertices[:, self.v3s, :]
+        cb1, l1 = self._perp(p1 - p0, p2 - p0, eps)
+        cb2, l2 = self._perp(p1 - p0, p3 - p0, eps)
+        cos = (cb1 * cb2).sum(-1) / (l1 * l2 + eps)
+        loss = (cos + 1).pow(2).sum(tuple(range(1, cos.dim())))
+        return loss.sum() / batch_size if self.average else loss
