@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward rendered images/s through the drop-in SoftRenderer (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2|C3|C5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch of synthetic input (SURVEY.md §8d, config C2 by
+default: 642-vertex / 1280-face CUB-like mesh, 256x256 render (512x512 raster), batch 16 per GPU,
+T2 = 36 surface textures):
+    verts = mean_shape + delta_v[b];  images = SoftRenderer(256, 'softmax')(verts, faces, cams, tex)
+    loss  = 2.5 * neg_iou_loss(alpha, mask) + 3.0 * texture_loss_masks(rgb, img, mask, alpha)
+    loss.backward()  -> d/d mean_shape [V,3], d/d texture [F,T2,3];  N>1: one NCCL all-reduce of the
+    flat [V*3 + F*T2*3] gradient.
+Rank 0 prints ONE JSON line.  `value` = images/s with inputs resident in HBM; `e2e` = the same step
+with that step's inputs copied from pinned host memory and the loss read back, inside the timed
+region.  `roofline` = raster backward kernel (the dominant one): algorithmic bytes / CUDA-event time of
+that kernel alone (events recorded by the C ABI around the launch), against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference` = the reference's own rasteriser code compiled for the host
+(oracle/_ref, "reference") or our CPU restatement (oracle B, "port") on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (subdiv, image_size, batch per GPU, tex_res)
+    "C2": dict(subdiv=3, image_size=256, batch=16, tex_res=6,
+               desc="CUB-like 642v/1280f mesh, 256x256 render, batch 16/GPU, silhouette+texture loss"),
+    "C3": dict(subdiv=3, image_size=512, batch=32, tex_res=6,
+               desc="CUB-like 642v/1280f mesh, 512x512 render, batch 32/GPU, silhouette+texture loss"),
+    "C5": dict(subdiv=4, image_size=1024, batch=8, tex_res=6,
+               desc="2562v/5120f mesh, 1024x1024 render, batch 8/GPU, silhouette+texture loss"),
+}
+NUM_SETS = 8  # rotating input sets so the step inputs exceed the 126 MB L2
+
+
+def alg_bytes_per_image(image_size, F, T2):
+    """compulsory fp32 traffic per rendered image at the soft_rasterize contract."""
+    fwd = F * (44 + 12 * T2) + 48 * image_size * image_size
+    bwd = 16 * image_size * image_size + F * (72 + 24 * T2)
+    return fwd, bwd
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (CPU; the ONLY place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_workload(cfg, batch, seed=0):
+    import numpy as np
+    from umr_b200 import synth
+    rng = np.random.default_rng(seed)
+    v, f = synth.icosphere(cfg["subdiv"])
+    verts = synth.bird_like(v, rng, batch)
+    cams = synth.cameras(rng, batch)
+    fv = synth.raster_space_faces(verts, f, cams)
+    tex = rng.uniform(0, 1, size=(batch, f.shape[0], cfg["tex_res"] ** 2, 3)).astype(np.float32)
+    g = rng.normal(size=(batch, 4, cfg["image_size"], cfg["image_size"])).astype(np.float32)
+    return fv, tex, g
+
+
+def cpu_reference_step(cfg, fv, tex, g, impl, nthreads):
+    """One fwd+bwd of the rasteriser core (prep + forward + 2x2 pool + backward) on the host."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import softras
+    img, fwd, rc = softras.render(fv, tex, cfg["image_size"], anti_aliasing=True, impl=impl, nthreads=nthreads,
+                                  aggr_func_rgb="softmax", sigma_val=1e-5, dist_eps=1e-10, gamma_val=1e-4)
+    softras.render_backward(fwd, rc, g, anti_aliasing=True, impl=impl, nthreads=nthreads)
+    return img
+
+
+def cpu_arm(cfg, steps, warmup, budget_s=None):
+    """Times the reference CPU path; returns (images_per_s, ms_per_step, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import softras
+    impl, kind = ("A", "reference") if softras.have_oracle_a() else ("B", "port")
+    cores = os.cpu_count() or 1
+    sub = 2  # bounded sample: a 2-image sub-batch of the workload per step
+    fv, tex, g = cpu_workload(cfg, sub)
+    for _ in range(max(warmup, 1)):
+        cpu_reference_step(cfg, fv, tex, g, impl, cores)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        cpu_reference_step(cfg, fv, tex, g, impl, cores)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    ips = done * sub / dt
+    info = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": "%d step(s) x %d-image sub-batch of %s, rasteriser core fwd+bwd (prep+forward+2x2 pool+"
+                      "backward), OpenMP over all host threads" % (done, sub, cfg["name"])}
+    return ips, dt / done * 1e3, info
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU workload
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, cfg, device, rank, seed=0):
+        import numpy as np
+        import torch
+        from umr_b200 import synth
+        from umr_b200.nnutils import smr
+        self.cfg, self.device = cfg, device
+        B, IS, R = cfg["batch"], cfg["image_size"], cfg["tex_res"]
+        v, f = synth.icosphere(cfg["subdiv"])
+        self.V, self.F, self.T2 = v.shape[0], f.shape[0], R * R
+        prng = np.random.default_rng(seed)            # shared parameters: identical on every rank
+        base = synth.bird_like(v, prng, 1, noise=0.0)[0]
+        self.mean_shape = torch.from_numpy(base).to(device).requires_grad_(True)
+        self.texture = torch.from_numpy(prng.uniform(0, 1, size=(self.F, self.T2, 3)).astype(np.float32)
+                                        ).to(device).requires_grad_(True)
+        self.faces = torch.from_numpy(f.astype(np.int64)).to(device)[None].repeat(B, 1, 1)
+        self.renderer = smr.SoftRenderer(IS, "softmax").to(device)
+        self.renderer.ambient_light_only()  # like MultiTextureLoss (loss_utils.py:286)
+        hard = smr.SoftRenderer(IS, "hard").to(device)
+        rng = np.random.default_rng(1000 + rank)      # per-rank data shard
+        self.host, self.dev = [], []
+        for _ in range(NUM_SETS):
+            delta = rng.normal(0, 0.02, size=(B, self.V, 3)).astype(np.float32)
+            cams = synth.cameras(rng, B)
+            imgs = synth.smooth_images(rng, B, IS)
+            # GT mask = hard-render alpha > 0.5 of the same mesh under a perturbed camera (§8d)
+            cams_gt = cams.copy()
+            cams_gt[:, 0] *= rng.uniform(0.9, 1.1, size=B).astype(np.float32)
+            cams_gt[:, 1:3] += rng.uniform(-0.05, 0.05, size=(B, 2)).astype(np.float32)
+            with torch.no_grad():
+                vv = self.mean_shape.detach()[None] + torch.from_numpy(delta).to(device)
+                a, _, _ = hard(vv, self.faces, torch.from_numpy(cams_gt).to(device))
+                masks = (a[:, 3] > 0.5).float().cpu()
+            h = [torch.from_numpy(delta).pin_memory(), torch.from_numpy(cams).pin_memory(),
+                 torch.from_numpy(imgs).pin_memory(), masks.pin_memory()]
+            self.host.append(h)
+            self.dev.append([t.to(device) for t in h])
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
+        self.flat_grad = torch.zeros(self.V * 3 + self.F * self.T2 * 3, device=device)
+        self.stage = [torch.empty_like(t, device=device) for t in self.host[0]]
+
+    def step(self, inputs, world):
+        import torch
+        from umr_b200.nnutils import loss_utils
+        delta, cams, imgs, masks = inputs
+        B = delta.shape[0]
+        self.mean_shape.grad = None
+        self.texture.grad = None
+        verts = self.mean_shape[None] + delta
+        tex = self.texture[None].expand(B, -1, -1, -1)
+        images, _, _ = self.renderer(verts, self.faces, cams, tex)
+        alpha, rgb = images[:, 3], images[:, :3]
+        loss = 2.5 * loss_utils.neg_iou_loss(alpha, masks) + 3.0 * loss_utils.texture_loss_masks(rgb, imgs, masks, alpha)
+        loss.backward()
+        n1 = self.V * 3
+        self.flat_grad[:n1].copy_(self.mean_shape.grad.reshape(-1))
+        self.flat_grad[n1:].copy_(self.texture.grad.reshape(-1))
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad)          # ONE NCCL all-reduce per step
+            self.flat_grad.mul_(1.0 / world)
+        return loss
+
+    def step_resident(self, i, world):
+        return self.step(self.dev[i % NUM_SETS], world)
+
+    def step_e2e(self, i, world):
+        h = self.host[i % NUM_SETS]
+        for s, t in zip(self.stage, h):
+            s.copy_(t, non_blocking=True)            # H2D from pinned memory, inside the timed region
+        loss = self.step(self.stage, world)
+        return float(loss.item())                    # D2H read of the step's result
+
+
+def run_gpu(args, cfg):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from umr_b200 import _lib, raster
+    lib = _lib.load()
+    torch.manual_seed(0)
+    wl = Workload(cfg, device, rank)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, profile=False):
+        for i in range(W):
+            fn(i, world)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = lib.umr_launch_count()
+        sink = [] if profile else None
+        raster.set_profile_sink(sink)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(W + i, world)
+        e1.record()
+        barrier()
+        raster.set_profile_sink(None)
+        ms = e0.elapsed_time(e1)
+        launches = lib.umr_launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        if dist is not None:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks, sink
+
+    ms_res, launches, clocks, sink = timed(wl.step_resident, profile=True)
+    kern = raster.collect_profile(sink)  # {"fwd": [ms...], "bwd": [ms...]}
+    ms_e2e, _, clocks_e2e, _ = timed(wl.step_e2e)
+
+    B = cfg["batch"]
+    total_images = B * world * K
+    value = total_images / (ms_res * 1e-3)
+    e2e = total_images / (ms_e2e * 1e-3)
+    fwd_b, bwd_b = alg_bytes_per_image(cfg["image_size"], wl.F, wl.T2)
+    peak, peak_src = measured_peak_gbs()
+    bwd_ms = sum(kern["bwd"]) / max(len(kern["bwd"]), 1)
+    fwd_ms = sum(kern["fwd"]) / max(len(kern["fwd"]), 1)
+    achieved = (bwd_b * B) / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
+    fwd_achieved = (fwd_b * B) / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+
+    out = {
+        "metric": "render fwd+bwd images/sec @256x256 1280-face mesh" if cfg["name"] == "C2"
+        else "render fwd+bwd images/sec (%s)" % cfg["name"],
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (cfg["name"], cfg["desc"]), "global_batch": B * world,
+                   "image_size": cfg["image_size"], "raster_size": 2 * cfg["image_size"], "faces": wl.F,
+                   "vertices": wl.V, "texture_res": cfg["tex_res"], "parallelism": "dp%d" % world,
+                   "l2": "inputs rotate over %d pre-generated batches (> 126 MB L2 together with the per-step "
+                         "buffers)" % NUM_SETS},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_raster_bwd<softmax,texgrad>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": peak_src, "kernel_ms": bwd_ms,
+                     "alg_bytes_per_launch": bwd_b * B,
+                     "fwd_kernel": {"kernel": "k_raster_fwd<softmax>", "kernel_ms": fwd_ms,
+                                    "achieved": fwd_achieved, "frac": fwd_achieved / peak if peak else None,
+                                    "alg_bytes_per_launch": fwd_b * B}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, _, info = cpu_arm(cfg, steps=64, warmup=1, budget_s=12.0)
+            out["cpu_baseline"] = info
+        except Exception as ex:  # the oracle is test infrastructure; never let it break the GPU number
+            out["cpu_baseline"] = {"value": None, "error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only; other ranks exit 0 without work
+    ips, ms, info = cpu_arm(cfg, steps=args.steps, warmup=max(args.warmup, 1))
+    fwd_b, bwd_b = alg_bytes_per_image(cfg["image_size"], 20 * 4 ** cfg["subdiv"], cfg["tex_res"] ** 2)
+    out = {"impl": "reference",
+           "metric": "render fwd+bwd images/sec @256x256 1280-face mesh" if cfg["name"] == "C2"
+           else "render fwd+bwd images/sec (%s)" % cfg["name"],
+           "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "%s: %s" % (cfg["name"], cfg["desc"]), "note": "CPU arm: each step is a bounded "
+                      "2-image sample of the workload (the reference has no CPU path of its own; this is its "
+                      "rasteriser code compiled for the host, or our restatement when that is unavailable)"},
+           "cpu_baseline": info,
+           "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config], name=args.config)
+    if args.impl == "reference":
+        if args.steps > 8:
+            args.steps = 8  # bounded: each CPU step is ~1 s
+        run_reference(args, cfg)
+    else:
+        run_gpu(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

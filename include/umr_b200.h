@@ -56,10 +56,22 @@ typedef struct UmrRasterParams {
     float near_plane, far_plane, eps, sigma_val, dist_eps, gamma_val;
     int32_t func_id_dist, func_id_rgb, func_id_alpha, texture_sample_type, double_side;
     float background_color[3];
+    /* optional profiling hooks: two cudaEvent_t (from umr_event_create) recorded on `stream`
+     * immediately before / after the main raster kernel of the call (NULL = off).  Used by bench.py
+     * to time the dominant kernel alone, live, without a profiler. */
+    void* ev_kernel_start;
+    void* ev_kernel_stop;
 } UmrRasterParams;
 
 const char* umr_error_string(int code);
 int umr_version(void);
+/* Number of kernels this library has launched in this process (all entry points, all threads). */
+uint64_t umr_launch_count(void);
+/* Thin event helpers so callers without a CUDA runtime binding can time on the launch stream. */
+int umr_event_create(void** event);
+int umr_event_destroy(void* event);
+int umr_event_record(void* event, void* stream);
+int umr_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
 
 /* Bytes of scratch `workspace` umr_raster_forward/backward need (256-byte aligned device memory). */
 size_t umr_raster_workspace_bytes(int32_t batch_size, int32_t num_faces);

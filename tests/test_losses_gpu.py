@@ -1,0 +1,125 @@
+"""GPU parity of the loss kernels (through the C ABI bindings) vs the torch-CPU oracles in
+oracle/losses.py.  Tolerance 1e-4 relative fp32 (+ small absolute floor)."""
+import numpy as np
+import pytest
+import torch
+
+import losses as oracle  # oracle/losses.py (test infrastructure)
+from umr_b200 import ops
+from umr_b200.nnutils import chamfer_python, geom_utils, loss_utils
+from util import rel_report
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _chk(name, got, ref, rtol=1e-4, atol=1e-6):
+    ok, msg = rel_report(name, got.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol, atol)
+    print(msg)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("C,H,W", [(3, 64, 64), (1, 48, 80), (3, 256, 256)])
+def test_sample_textures(C, H, W):
+    g = torch.Generator().manual_seed(0)
+    B, F, T = 2, 50, 6
+    img = torch.rand(B, C, H, W, generator=g)
+    flow = torch.rand(B, F, T, T, 2, generator=g) * 2.4 - 1.2  # includes out-of-range samples (zero padding)
+    flow_ref = flow.clone().requires_grad_(True)
+    img_ref = img.clone().requires_grad_(True)
+    ref = oracle.sample_textures(flow_ref, img_ref)
+    w = torch.rand(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    flow_g = flow.to(DEV).requires_grad_(True)
+    img_g = img.to(DEV).requires_grad_(True)
+    got = geom_utils.sample_textures(flow_g, img_g)
+    assert got.shape == ref.shape
+    (got * w.to(DEV)).sum().backward()
+    _chk("sample fwd", got, ref)
+    _chk("sample dflow", flow_g.grad, flow_ref.grad, 1e-4, 1e-4 * float(flow_ref.grad.abs().max()) * 1e-2 + 1e-6)
+    _chk("sample dimage", img_g.grad, img_ref.grad, 1e-4, 1e-5)
+
+
+def test_texture_dt_loss():
+    g = torch.Generator().manual_seed(1)
+    dt = torch.rand(3, 1, 64, 64, generator=g)
+    flow = (torch.rand(3, 40, 6, 6, 2, generator=g) * 2 - 1)
+    fr = flow.clone().requires_grad_(True)
+    ref = oracle.texture_dt_loss(fr, dt)
+    ref.backward()
+    fg = flow.to(DEV).requires_grad_(True)
+    got = loss_utils.texture_dt_loss(fg, dt.to(DEV))
+    got.backward()
+    _chk("tex_dt", got, ref)
+    _chk("tex_dt dflow", fg.grad, fr.grad, 1e-4, 1e-9)
+
+
+@pytest.mark.parametrize("shape,avg", [((4, 64, 64), False), ((4, 64, 64), True), ((3, 37, 41), False), ((2, 256, 256), True)])
+def test_neg_iou(shape, avg):
+    g = torch.Generator().manual_seed(2)
+    p = torch.rand(shape, generator=g)
+    t = (torch.rand(shape, generator=g) > 0.5).float()
+    pr = p.clone().requires_grad_(True)
+    ref = oracle.neg_iou_loss(pr, t, avg=avg)
+    wgt = torch.rand(ref.shape, generator=g) if not avg else torch.tensor(1.0)
+    (ref * wgt).sum().backward()
+    pg = p.to(DEV).requires_grad_(True)
+    got = loss_utils.neg_iou_loss(pg, t.to(DEV), avg=avg)
+    (got * wgt.to(DEV)).sum().backward()
+    _chk("iou", got, ref)
+    _chk("iou dp", pg.grad, pr.grad, 1e-4, 1e-10)
+
+
+@pytest.mark.parametrize("B,N,M,D", [(4, 40, 10, 2), (3, 80, 30, 2), (1, 5000, 642, 2), (2, 33, 7, 3)])
+def test_chamfer(B, N, M, D):
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(B, N, D, generator=g) - 0.5
+    b = torch.rand(B, M, D, generator=g) - 0.5
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    r = oracle.dist_chamfer(ar, br)
+    w1, w2 = torch.rand(B, N, generator=g), torch.rand(B, M, generator=g)
+    ((r[0] * w1).sum() + (r[1] * w2).sum()).backward()
+    ag, bg = a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    o = chamfer_python.distChamfer(ag, bg)
+    ((o[0] * w1.to(DEV)).sum() + (o[1] * w2.to(DEV)).sum()).backward()
+    assert o[2].dtype == torch.int32 and o[3].dtype == torch.int32
+    _chk("d_ab", o[0], r[0], 1e-4, 1e-6)
+    _chk("d_ba", o[1], r[1], 1e-4, 1e-6)
+    # argmin: identical unless two candidates tie within rounding of the expanded form
+    for k in (2, 3):
+        mism = (o[k].cpu() != r[k]).float().mean().item()
+        print("argmin mismatch frac", mism)
+        assert mism < 1e-3
+    _chk("da", ag.grad, ar.grad, 1e-4, 1e-5)
+    _chk("db", bg.grad, br.grad, 1e-4, 1e-4)
+
+
+def test_chamfer_ties_lowest_index():
+    a = torch.zeros(1, 3, 2)
+    b = torch.tensor([[[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0], [0.0, -1.0]]])
+    o = chamfer_python.distChamfer(a.to(DEV), b.to(DEV))
+    assert o[2].cpu().tolist() == [[0, 0, 0]]
+    assert o[3].cpu().tolist() == [[0, 0, 0, 0]]
+
+
+def test_tex_cycle():
+    g = torch.Generator().manual_seed(4)
+    B, F, T, P = 3, 64, 6, 32 * 32
+    flow = torch.rand(B, F, T, T, 2, generator=g) * 2 - 1
+    prob = torch.rand(B, F, 2, generator=g) * 2 - 1
+    ids = torch.randint(-1, F // 2, (B, P), generator=g).float()   # -1 = background, upper half never visible
+    ids[2] = 5.0                                                    # one sample without background
+    fr = flow.clone().requires_grad_(True)
+    ref, vis_ref = oracle.tex_cycle(fr, prob, ids)
+    ref.backward()
+    fg = flow.to(DEV).requires_grad_(True)
+    got, vis = loss_utils.TexCycle()(fg, prob.to(DEV), ids.to(DEV))
+    got.backward()
+    _chk("texcycle", got, ref)
+    _chk("texcycle vis", vis, vis_ref, 1e-5, 1e-7)
+    _chk("texcycle dflow", fg.grad, fr.grad, 1e-4, 1e-9)
+
+
+def test_ops_reject_cpu():
+    with pytest.raises(TypeError):
+        ops.bilinear_sample(torch.zeros(1, 1, 4, 4), torch.zeros(1, 3, 2))

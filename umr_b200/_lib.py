@@ -21,13 +21,19 @@ class UmrRasterParams(ctypes.Structure):
                 ("sigma_val", ctypes.c_float), ("dist_eps", ctypes.c_float), ("gamma_val", ctypes.c_float),
                 ("func_id_dist", ctypes.c_int32), ("func_id_rgb", ctypes.c_int32),
                 ("func_id_alpha", ctypes.c_int32), ("texture_sample_type", ctypes.c_int32),
-                ("double_side", ctypes.c_int32), ("background_color", ctypes.c_float * 3)]
+                ("double_side", ctypes.c_int32), ("background_color", ctypes.c_float * 3),
+                ("ev_kernel_start", ctypes.c_void_p), ("ev_kernel_stop", ctypes.c_void_p)]
 
 
 EXPORTS = {
     # name: (restype, argtypes)
     "umr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "umr_version": (ctypes.c_int, []),
+    "umr_launch_count": (ctypes.c_uint64, []),
+    "umr_event_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
+    "umr_event_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "umr_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "umr_event_elapsed_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "umr_raster_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
     "umr_raster_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
                                                         ctypes.c_void_p]),

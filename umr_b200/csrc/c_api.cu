@@ -16,3 +16,24 @@ extern "C" const char* umr_error_string(int code) {
 }
 
 extern "C" int umr_version(void) { return 100; }
+
+#include <atomic>
+namespace umr { std::atomic<unsigned long long> g_launches{0}; }
+extern "C" uint64_t umr_launch_count(void) { return umr::g_launches.load(); }
+extern "C" int umr_event_create(void** event) {
+    if (!event) return UMR_ERR_BAD_ARG;
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    *event = (void*)e;
+    return (int)rc;
+}
+extern "C" int umr_event_destroy(void* event) { return (int)cudaEventDestroy((cudaEvent_t)event); }
+extern "C" int umr_event_record(void* event, void* stream) {
+    return (int)cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream);
+}
+extern "C" int umr_event_elapsed_ms(void* start, void* stop, float* ms) {
+    if (!ms) return UMR_ERR_BAD_ARG;
+    cudaError_t rc = cudaEventSynchronize((cudaEvent_t)stop);
+    if (rc != cudaSuccess) return (int)rc;
+    return (int)cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop);
+}

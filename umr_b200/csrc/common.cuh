@@ -4,7 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 namespace umr {
+extern std::atomic<unsigned long long> g_launches;  // c_api.cu; read through umr_launch_count()
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

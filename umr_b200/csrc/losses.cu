@@ -280,6 +280,7 @@ extern "C" int umr_bilinear_sample_forward(const float* image, const float* flow
     cudaStream_t st = (cudaStream_t)stream_;
     const dim3 grid((N + 255) / 256, B);
     const float2* fl = reinterpret_cast<const float2*>(flow);
+    count_launch();
     switch (C) {
         case 1: k_sample_fwd<1><<<grid, 256, 0, st>>>(image, fl, out, H, W, N); break;
         case 2: k_sample_fwd<2><<<grid, 256, 0, st>>>(image, fl, out, H, W, N); break;
@@ -304,6 +305,7 @@ extern "C" int umr_bilinear_sample_backward(const float* image, const float* flo
     const dim3 grid((N + 255) / 256, B);
     const float2* fl = reinterpret_cast<const float2*>(flow);
     float2* gf = reinterpret_cast<float2*>(grad_flow);
+    count_launch();
     switch (C) {
         case 1: k_sample_bwd<1><<<grid, 256, 0, st>>>(image, fl, grad_out, gf, grad_image, H, W, N); break;
         case 2: k_sample_bwd<2><<<grid, 256, 0, st>>>(image, fl, grad_out, gf, grad_image, H, W, N); break;
@@ -324,8 +326,8 @@ extern "C" int umr_iou_forward(const float* predict, const float* target, float*
     e = cudaMemsetAsync(uni, 0, (size_t)B * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     const dim3 grid((unsigned)((N + IOU_PER_CTA - 1) / IOU_PER_CTA), B);
-    k_iou_partial<<<grid, IOU_THREADS, 0, st>>>(predict, target, inter, uni, N);
-    k_iou_finalize<<<(B + 127) / 128, 128, 0, st>>>(inter, uni, loss, B);
+    count_launch(); k_iou_partial<<<grid, IOU_THREADS, 0, st>>>(predict, target, inter, uni, N);
+    count_launch(); k_iou_finalize<<<(B + 127) / 128, 128, 0, st>>>(inter, uni, loss, B);
     UMR_RET_LAST();
 }
 
@@ -336,7 +338,7 @@ extern "C" int umr_iou_backward(const float* target, const float* inter, const f
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t blocks = (N + 256 * 4 - 1) / (256 * 4);
     const dim3 grid((unsigned)(blocks < 1 ? 1 : (blocks > 1024 ? 1024 : blocks)), B);
-    k_iou_bwd<<<grid, 256, 0, st>>>(target, inter, uni, grad_loss, grad_predict, N);
+    count_launch(); k_iou_bwd<<<grid, 256, 0, st>>>(target, inter, uni, grad_loss, grad_predict, N);
     UMR_RET_LAST();
 }
 
@@ -348,11 +350,11 @@ extern "C" int umr_chamfer_forward(const float* a, const float* b, float* dist_a
     cudaStream_t st = (cudaStream_t)stream_;
     const dim3 g1((N + 7) / 8, B), g2((M + 7) / 8, B);
     if (D == 2) {
-        k_chamfer_nn<2><<<g1, 256, 0, st>>>(a, b, dist_ab, idx_ab, N, M);
-        k_chamfer_nn<2><<<g2, 256, 0, st>>>(b, a, dist_ba, idx_ba, M, N);
+        count_launch(); k_chamfer_nn<2><<<g1, 256, 0, st>>>(a, b, dist_ab, idx_ab, N, M);
+        count_launch(); k_chamfer_nn<2><<<g2, 256, 0, st>>>(b, a, dist_ba, idx_ba, M, N);
     } else {
-        k_chamfer_nn<3><<<g1, 256, 0, st>>>(a, b, dist_ab, idx_ab, N, M);
-        k_chamfer_nn<3><<<g2, 256, 0, st>>>(b, a, dist_ba, idx_ba, M, N);
+        count_launch(); k_chamfer_nn<3><<<g1, 256, 0, st>>>(a, b, dist_ab, idx_ab, N, M);
+        count_launch(); k_chamfer_nn<3><<<g2, 256, 0, st>>>(b, a, dist_ba, idx_ba, M, N);
     }
     UMR_RET_LAST();
 }
@@ -371,11 +373,13 @@ extern "C" int umr_chamfer_backward(const float* a, const float* b, const int32_
     const dim3 g1((N + 255) / 256, B), g2((M + 255) / 256, B);
     if (grad_dist_ab) {
         if (!idx_ab) return UMR_ERR_BAD_ARG;
+        count_launch();
         if (D == 2) k_chamfer_bwd<2><<<g1, 256, 0, st>>>(a, b, idx_ab, grad_dist_ab, grad_a, grad_b, N, M);
         else k_chamfer_bwd<3><<<g1, 256, 0, st>>>(a, b, idx_ab, grad_dist_ab, grad_a, grad_b, N, M);
     }
     if (grad_dist_ba) {
         if (!idx_ba) return UMR_ERR_BAD_ARG;
+        count_launch();
         if (D == 2) k_chamfer_bwd<2><<<g2, 256, 0, st>>>(b, a, idx_ba, grad_dist_ba, grad_b, grad_a, M, N);
         else k_chamfer_bwd<3><<<g2, 256, 0, st>>>(b, a, idx_ba, grad_dist_ba, grad_b, grad_a, M, N);
     }
@@ -393,10 +397,10 @@ extern "C" int umr_texcycle_forward(const float* flow, const float* prob, const 
     e = cudaMemsetAsync(loss, 0, sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     const int64_t blocks = (P + 255) / 256;
-    k_visible<<<dim3((unsigned)(blocks > 2048 ? 2048 : blocks), B), 256, 0, st>>>(face_ids, visible, F, P);
+    count_launch(); k_visible<<<dim3((unsigned)(blocks > 2048 ? 2048 : blocks), B), 256, 0, st>>>(face_ids, visible, F, P);
     const int n = B * F;
     const float scale = 1.f / ((float)n * 2.f);  // MSELoss mean over B*F*2 elements
-    k_texcycle_fwd<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(flow),
+    count_launch(); k_texcycle_fwd<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(flow),
                                                     reinterpret_cast<const float2*>(prob), visible, loss, n, T2, scale);
     UMR_RET_LAST();
 }
@@ -407,7 +411,7 @@ extern "C" int umr_texcycle_backward(const float* flow, const float* prob, const
     cudaStream_t st = (cudaStream_t)stream_;
     const int n = B * F;
     const float scale = 1.f / ((float)n * 2.f);
-    k_texcycle_bwd<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(flow),
+    count_launch(); k_texcycle_bwd<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(flow),
                                                     reinterpret_cast<const float2*>(prob), visible, grad_loss,
                                                     reinterpret_cast<float2*>(grad_flow), n, T2, scale);
     UMR_RET_LAST();

@@ -738,6 +738,7 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     const int n = B * F;
     const float r = sqrtf(K.thr);  // kernel.cu:355 sqrt(threshold) in float
     k_prep<<<(n + 255) / 256, 256, 0, stream>>>(face_vertices, rec, box, n, r);
+    count_launch();
     const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
     const bool want_p2f = p2f_info != nullptr;
     if (want_p2f && softmax) {
@@ -746,6 +747,8 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     }
     const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
     const size_t smem = raster_dyn_smem(F);
+    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
+    count_launch();
     if (softmax) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(k_raster_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -760,8 +763,10 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
                                                      nullptr, K, p->eps, p->background_color[0],
                                                      p->background_color[1], p->background_color[2]);
     }
+    if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
     if (want_p2f) {
         if (softmax) {
+            count_launch();
             k_p2f_finalize<<<(n + 255) / 256, 256, 0, stream>>>(p2f_acc, p2f_info, (size_t)n);
         } else {  // hard mode never accumulates p2f (kernel.cu:417-431 is softmax-only) -> zeros
             cudaError_t e = cudaMemsetAsync(p2f_info, 0, (size_t)n * 2 * sizeof(float), stream);
@@ -792,6 +797,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     const float r = sqrtf(K.thr);
     // the workspace is scratch (another render may have used it since forward): rebuild the records
     k_prep<<<(n + 255) / 256, 256, 0, stream>>>(face_vertices, rec, box, n, r);
+    count_launch();
     cudaError_t e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
     if (e != cudaSuccess) return (int)e;
     if (grad_textures) {
@@ -809,11 +815,14 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                             grad_images, grad_faces, grad_textures, K); \
     } while (0)
+    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
+    count_launch();
     if (softmax) {
         if (grad_textures) UMR_LAUNCH_BWD(1, true); else UMR_LAUNCH_BWD(1, false);
     } else {
         if (grad_textures) UMR_LAUNCH_BWD(0, true); else UMR_LAUNCH_BWD(0, false);
     }
 #undef UMR_LAUNCH_BWD
+    if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
     return (int)cudaGetLastError();
 }

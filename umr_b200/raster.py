@@ -22,6 +22,41 @@ FUNC_ALPHA = {"hard": 0, "sum": 1, "prod": 2}
 FUNC_SAMPLE = {"surface": 0, "vertex": 1}
 
 
+# --- optional live kernel timing (bench.py): the C ABI records a cudaEvent pair around the main raster
+# kernel of every forward / backward call while a sink is installed ------------------------------
+_profile_sink = None
+
+
+def set_profile_sink(sink):
+    """sink: a list that receives (kind, start_event, stop_event) per raster call, or None to stop."""
+    global _profile_sink
+    _profile_sink = sink
+
+
+def _attach_events(params, kind):
+    if _profile_sink is None:
+        return
+    lib = _lib.load()
+    a, b = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(lib.umr_event_create(ctypes.byref(a)), "umr_event_create")
+    _lib.check(lib.umr_event_create(ctypes.byref(b)), "umr_event_create")
+    params.ev_kernel_start, params.ev_kernel_stop = a.value, b.value
+    _profile_sink.append((kind, a, b))
+
+
+def collect_profile(sink):
+    """Elapsed milliseconds of every recorded kernel, grouped by kind; destroys the events."""
+    lib = _lib.load()
+    out = {"fwd": [], "bwd": []}
+    for kind, a, b in sink or []:
+        ms = ctypes.c_float()
+        _lib.check(lib.umr_event_elapsed_ms(a, b, ctypes.byref(ms)), "umr_event_elapsed_ms")
+        out[kind].append(float(ms.value))
+        lib.umr_event_destroy(a)
+        lib.umr_event_destroy(b)
+    return out
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -70,6 +105,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
                              eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb,
                              aggr_func_alpha, texture_type)
         need_bwd = face_vertices.requires_grad or textures.requires_grad
+        _attach_events(params, "fwd")
         with torch.cuda.device(dev):
             images = torch.empty(B, 4, image_size, image_size, device=dev, dtype=torch.float32)
             if anti_aliasing:
@@ -84,6 +120,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
                                         _ptr(aggrs), _ptr(p2f), ctypes.byref(params), _ptr(ws),
                                         _stream_ptr(dev))
         _lib.check(rc, "umr_raster_forward")
+        params.ev_kernel_start = params.ev_kernel_stop = None
         ctx.params = params
         ctx.in_shape = tuple(face_vertices.shape)
         ctx.tex_needs_grad = textures.requires_grad
@@ -99,6 +136,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
         dev = fv.device
         B, F = fv.shape[:2]
         g = grad_images.contiguous().float()
+        _attach_events(ctx.params, "bwd")
         with torch.cuda.device(dev):
             grad_faces = torch.empty_like(fv)
             grad_tex = torch.empty_like(tex) if ctx.tex_needs_grad else None
@@ -107,6 +145,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
                                          _ptr(grad_faces), _ptr(grad_tex), ctypes.byref(ctx.params),
                                          _ptr(ws), _stream_ptr(dev))
         _lib.check(rc, "umr_raster_backward")
+        ctx.params.ev_kernel_start = ctx.params.ev_kernel_stop = None
         return (grad_faces.view(ctx.in_shape), grad_tex) + (None,) * 14
 
 
