@@ -200,7 +200,8 @@ class Workload:
             self.host.append(h)
             self.dev.append([t.to(device) for t in h])
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
-        self.flat_grad = torch.zeros(self.V * 3 + self.F * self.T2 * 3, device=device)
+        from umr_b200.dist import FlatGradAllReduce
+        self.reducer = FlatGradAllReduce([self.mean_shape, self.texture], average=True)
         self.stage = [torch.empty_like(t, device=device) for t in self.host[0]]
 
     def step(self, inputs, world):
@@ -216,13 +217,7 @@ class Workload:
         alpha, rgb = images[:, 3], images[:, :3]
         loss = 2.5 * loss_utils.neg_iou_loss(alpha, masks) + 3.0 * loss_utils.texture_loss_masks(rgb, imgs, masks, alpha)
         loss.backward()
-        n1 = self.V * 3
-        self.flat_grad[:n1].copy_(self.mean_shape.grad.reshape(-1))
-        self.flat_grad[n1:].copy_(self.texture.grad.reshape(-1))
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grad)          # ONE NCCL all-reduce per step
-            self.flat_grad.mul_(1.0 / world)
+        self.reducer()  # N>1: ONE NCCL all-reduce of the flat [V*3 + F*T2*3] gradient
         return loss
 
     def step_resident(self, i, world):
