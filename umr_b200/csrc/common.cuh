@@ -49,6 +49,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
         : "memory");
 }
 
+// Ampere-style 16-byte async copy global -> shared (SASS: LDGSTS), L2-only caching
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);

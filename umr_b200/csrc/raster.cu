@@ -118,8 +118,13 @@ struct Frag {
     float sign, dx, dy, dis, D;
 };
 
-__device__ __forceinline__ float pixel_coord(int i, int S) {  // kernel.cu:325-326 (double, then float)
-    return (float)((2. * i + 1. - S) / S);
+// kernel.cu:325-326 evaluates (2.*i + 1. - S) / S in double and stores a float.  Numerator and
+// denominator are integers < 2^24 (exact in float), and rounding a correctly rounded binary64 quotient
+// to binary32 equals the correctly rounded binary32 quotient whenever the wide format carries at least
+// 2p+2 = 50 bits (Figueroa's double-rounding theorem; binary64 has 53).  So one IEEE float division is
+// bit-identical and ~4x cheaper than the double one.
+__device__ __forceinline__ float pixel_coord(int i, int S) {
+    return __fdiv_rn((float)(2 * i + 1 - S), (float)S);
 }
 
 // euclidean signed distance + sigmoid: kernel.cu:62-152, 380-383.  `rc` points at a staged record.
@@ -241,7 +246,9 @@ __device__ __forceinline__ void clip_bary(float& w0, float& w1, float& w2) {  //
 }
 
 __device__ __forceinline__ float depth_of(const float* __restrict__ rc, float c0, float c1, float c2) {
-    return (float)(1. / (double)(c0 / rc[2] + c1 / rc[5] + c2 / rc[8]));  // kernel.cu:403
+    // kernel.cu:403: 1. / (float sum) in double, stored as float == 1.f / sum in float (same theorem:
+    // both operands are floats, the binary64 quotient is rounded once more to binary32).
+    return __fdiv_rn(1.f, c0 / rc[2] + c1 / rc[5] + c2 / rc[8]);
 }
 
 __device__ __forceinline__ int texel_index(float c0, float c1, int R) {  // kernel.cu:180-190
@@ -254,57 +261,80 @@ __device__ __forceinline__ int texel_index(float c0, float c1, int R) {  // kern
 // ---------------------------------------------------------------------------------------------
 // tile machinery shared by forward and backward
 // ---------------------------------------------------------------------------------------------
-struct TileSmem {
-    // dynamic shared memory layout (bytes):  [ records NSTAGE*CHUNK*128 | list u16[F_pad] ]
-    float* rec;       // NSTAGE * CHUNK * REC_F floats
-    uint16_t* list;   // ordered face indices touching the tile
-};
+constexpr int BOX_PIECE = 2048;  // cull boxes staged per TMA bulk copy (32 KB)
+constexpr int NWARP = CTA / 32;
 
-// Ordered compaction of the faces whose cull box touches the tile.  Returns the list length
-// (uniform across the CTA).  box: [F] float4 of this image.
+// dynamic shared memory: [ records NSTAGE*CHUNK*128 B | cull boxes min(F,BOX_PIECE)*16 B | list u16[F] ]
+__host__ __device__ inline size_t smem_box_off() { return (size_t)NSTAGE * CHUNK * REC_F * 4; }
+__host__ __device__ inline size_t smem_list_off(int F) {
+    return smem_box_off() + (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16;
+}
+
+// Ordered compaction of the faces whose cull box touches the tile.  The image's cull boxes are
+// contiguous in HBM/L2, so each piece (<= 2048 faces, 32 KB) is staged with ONE TMA bulk copy signalled
+// on an mbarrier; the scan then runs out of shared memory.  Each warp owns a contiguous run of the
+// piece (ascending face order = warp-major, round, lane), keeps its ballots in registers, and one
+// barrier per piece turns the per-warp counts into list offsets.  Returns the list length (uniform).
 __device__ __forceinline__ int build_tile_list(const float4* __restrict__ box, int F, float tx_first,
-                                               float tx_last, float ty_bot, float ty_top,
-                                               uint16_t* list, int* s_warp_cnt, int* s_total) {
+                                               float tx_last, float ty_bot, float ty_top, float4* s_box,
+                                               uint16_t* list, int* s_warp_cnt, uint64_t* bar) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int total = 0;
-    for (int base = 0; base < F; base += CTA) {
-        const int f = base + tid;
-        bool hit = false;
-        if (f < F) {
-            const float4 bb = __ldg(box + f);
-            hit = !(tx_first > bb.y || tx_last < bb.x || ty_bot > bb.w || ty_top < bb.z);
+    uint32_t phase = 0;
+    for (int base = 0; base < F; base += BOX_PIECE) {
+        const int P = min(BOX_PIECE, F - base);
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)P * 16u);
+            tma_bulk_g2s(s_box, box + base, (uint32_t)P * 16u, bar);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        const int per = ((P + NWARP * 32 - 1) / (NWARP * 32)) * 32;  // faces per warp, multiple of 32, <= 256
+        uint32_t masks[BOX_PIECE / (NWARP * 32)];
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < BOX_PIECE / (NWARP * 32); ++r) {
+            const int f = warp * per + r * 32 + lane;
+            bool hit = false;
+            if (r * 32 < per && f < P) {
+                const float4 bb = s_box[f];
+                hit = !(tx_first > bb.y || tx_last < bb.x || ty_bot > bb.w || ty_top < bb.z);
+            }
+            masks[r] = __ballot_sync(0xffffffffu, hit);
+            cnt += __popc(masks[r]);
+        }
+        if (lane == 0) s_warp_cnt[warp] = cnt;
         __syncthreads();
         int off = total;
 #pragma unroll
-        for (int w = 0; w < CTA / 32; ++w) {
+        for (int w = 0; w < NWARP; ++w) {
             const int c = s_warp_cnt[w];
             if (w < warp) off += c;
             total += c;
         }
-        if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)f;
-        __syncthreads();
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int r = 0; r < BOX_PIECE / (NWARP * 32); ++r) {
+            if ((masks[r] >> lane) & 1u) list[off + __popc(masks[r] & lt)] = (uint16_t)(base + warp * per + r * 32 + lane);
+            off += __popc(masks[r]);
+        }
+        __syncthreads();  // list visible; s_box / s_warp_cnt reusable
     }
-    (void)s_total;
     return total;
 }
 
-// issue the TMA bulk copies of chunk c (records list[c*CHUNK ...]) into stage c % NSTAGE; warp 0 only
+// Gather chunk c of the tile list (32 records x 128 B, scattered in L2) into stage c % NSTAGE with one
+// 16-byte cp.async per thread (8 consecutive threads fetch one 128-byte record = one cache line).
+// Always commits a group so every thread's group count stays uniform.
 __device__ __forceinline__ void issue_chunk(const float* __restrict__ rec_img, const uint16_t* list, int n,
-                                            int c, float* s_rec, uint64_t* bars) {
-    const int lane = threadIdx.x & 31;
-    const int st = c % NSTAGE;
-    const int begin = c * CHUNK;
-    const int cnt = min(CHUNK, n - begin);
-    if (lane == 0) mbar_arrive_expect_tx(&bars[st], (uint32_t)cnt * REC_F * 4u);
-    __syncwarp();
-    if (lane < cnt) {
-        const int f = list[begin + lane];
-        tma_bulk_g2s(s_rec + ((size_t)st * CHUNK + lane) * REC_F, rec_img + (size_t)f * REC_F,
-                     REC_F * 4u, &bars[st]);
+                                            int c, float* s_rec) {
+    const int j = threadIdx.x >> 3, q = threadIdx.x & 7;
+    const int idx = c * CHUNK + j;
+    if (idx < n) {
+        const int f = list[idx];
+        cp_async16(s_rec + ((size_t)(c % NSTAGE) * CHUNK + j) * REC_F + q * 4, rec_img + (size_t)f * REC_F + q * 4);
     }
+    cp_async_commit();
 }
 
 struct Consts {
@@ -316,7 +346,7 @@ struct Consts {
 // forward
 // =============================================================================================
 template <int RGB>  // 1 softmax, 0 hard
-__global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ rec_all,
+__global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__ rec_all,
                                                     const float4* __restrict__ box_all,
                                                     const float* __restrict__ textures,
                                                     float* __restrict__ images, float* __restrict__ colors_hi,
@@ -324,10 +354,11 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
                                                     Consts K, float eps, float bg0, float bg1, float bg2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NSTAGE * CHUNK * REC_F * 4);
-    __shared__ uint64_t s_bar[NSTAGE];
-    __shared__ int s_warp_cnt[CTA / 32];
-    __shared__ float s_p2f[CHUNK][3];
+    float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + smem_list_off(K.F));
+    __shared__ uint64_t s_bar;
+    __shared__ int s_warp_cnt[NWARP];
+    __shared__ float s_p2f[NWARP][CHUNK][3];  // per-warp partial sums: no shared atomics
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
@@ -340,10 +371,10 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
     const float yp = pixel_coord(S - 1 - py, S);
 
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_bar[s], 1);
+        mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
+    __syncthreads();
     // tile extents in pixel-centre coordinates (monotone in the index, so the test is conservative)
     const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
     const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
@@ -352,8 +383,8 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
 
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_list, s_warp_cnt, nullptr);
-    // (build_tile_list ends with __syncthreads: barrier init + list are visible)
+    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_box, s_list, s_warp_cnt, &s_bar);
+    // (build_tile_list ends with __syncthreads: the list is visible)
 
     // pixel state (kernel.cu:335-348)
     float acc_a = 1.f;  // prod alpha accumulator
@@ -366,9 +397,9 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
     int fid = -1;
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
-    if (warp == 0) {
-        if (nchunk > 0) issue_chunk(rec_img, s_list, n, 0, s_rec, s_bar);
-        if (nchunk > 1) issue_chunk(rec_img, s_list, n, 1, s_rec, s_bar);
+    if (nchunk > 0) {
+        issue_chunk(rec_img, s_list, n, 0, s_rec);
+        issue_chunk(rec_img, s_list, n, 1, s_rec);
     }
     const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
     // torch-1.1 affine_grid (align_corners=True) coordinates of this pixel: linspace(-1, 1, S)
@@ -379,9 +410,13 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % NSTAGE;
         const int cnt = min(CHUNK, n - c * CHUNK);
-        if (RGB == 1 && tid < CHUNK * 3) (&s_p2f[0][0])[tid] = 0.f;
-        mbar_wait(&s_bar[st], (uint32_t)((c / NSTAGE) & 1));
-        if (RGB == 1) __syncthreads();  // s_p2f zero visible
+        if (RGB == 1) {
+#pragma unroll
+            for (int i = lane; i < CHUNK * 3; i += 32) (&s_p2f[warp][0][0])[i] = 0.f;  // own slice only
+            __syncwarp();
+        }
+        cp_async_wait<1>();  // chunk c has landed (c+1 may still be in flight)
+        __syncthreads();
         const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
         for (int j = 0; j < cnt; ++j) {
             const float* rc = chunk + j * REC_F;
@@ -431,9 +466,9 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
                 if (__any_sync(0xffffffffu, contrib)) {
                     a_x = warp_sum(a_x); a_y = warp_sum(a_y); a_w = warp_sum(a_w);
                     if (lane == 0) {
-                        atomicAdd(&s_p2f[j][0], a_x);
-                        atomicAdd(&s_p2f[j][1], a_y);
-                        atomicAdd(&s_p2f[j][2], a_w);
+                        s_p2f[warp][j][0] += a_x;
+                        s_p2f[warp][j][1] += a_y;
+                        s_p2f[warp][j][2] += a_w;
                     }
                 }
             }
@@ -441,10 +476,12 @@ __global__ void __launch_bounds__(CTA) k_raster_fwd(const float* __restrict__ re
         __syncthreads();  // everyone is done with stage st (and s_p2f is complete)
         if (RGB == 1 && p2f_acc != nullptr && tid < cnt * 3) {
             const int j = tid / 3, k = tid - j * 3;
-            const float v = s_p2f[j][k];
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) v += s_p2f[w][j][k];
             if (v != 0.f) atomicAdd(p2f_acc + ((size_t)b * F + s_list[c * CHUNK + j]) * 4 + k, v);
         }
-        if (warp == 0 && c + NSTAGE < nchunk) issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec, s_bar);
+        issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);  // commits an empty group past the end
         if (RGB == 1) __syncthreads();  // s_p2f flushed before the next chunk zeroes it
     }
 
@@ -508,7 +545,7 @@ __global__ void k_p2f_finalize(const float* __restrict__ acc, float* __restrict_
 // backward
 // =============================================================================================
 template <int RGB, bool TEXGRAD>
-__global__ void __launch_bounds__(CTA) k_raster_bwd(const float* __restrict__ rec_all,
+__global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__ rec_all,
                                                     const float4* __restrict__ box_all,
                                                     const float* __restrict__ textures,
                                                     const float* __restrict__ colors_hi,
@@ -518,10 +555,11 @@ __global__ void __launch_bounds__(CTA) k_raster_bwd(const float* __restrict__ re
                                                     Consts K) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NSTAGE * CHUNK * REC_F * 4);
-    __shared__ uint64_t s_bar[NSTAGE];
-    __shared__ int s_warp_cnt[CTA / 32];
-    __shared__ float s_g[CHUNK][9];
+    float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + smem_list_off(K.F));
+    __shared__ uint64_t s_bar;
+    __shared__ int s_warp_cnt[NWARP];
+    __shared__ float s_g[NWARP][CHUNK][9];  // per-warp partial gradients: no shared atomics
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
@@ -533,24 +571,22 @@ __global__ void __launch_bounds__(CTA) k_raster_bwd(const float* __restrict__ re
     const float yp = pixel_coord(S - 1 - py, S);
 
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_bar[s], 1);
+        mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
+    __syncthreads();
     const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
     const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
     const float tx_first = pixel_coord(blockIdx.x * TILE, S), tx_last = pixel_coord(x_last_i, S);
     const float ty_top = pixel_coord(S - 1 - blockIdx.y * TILE, S), ty_bot = pixel_coord(S - 1 - y_last_i, S);
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_list, s_warp_cnt, nullptr);
+    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_box, s_list, s_warp_cnt, &s_bar);
     if (n == 0) return;  // uniform
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
-    if (warp == 0) {
-        issue_chunk(rec_img, s_list, n, 0, s_rec, s_bar);
-        if (nchunk > 1) issue_chunk(rec_img, s_list, n, 1, s_rec, s_bar);
-    }
+    issue_chunk(rec_img, s_list, n, 0, s_rec);
+    issue_chunk(rec_img, s_list, n, 1, s_rec);
 
     // per-pixel inputs
     const size_t np = (size_t)S * S;
@@ -583,8 +619,10 @@ __global__ void __launch_bounds__(CTA) k_raster_bwd(const float* __restrict__ re
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % NSTAGE;
         const int cnt = min(CHUNK, n - c * CHUNK);
-        for (int i = tid; i < CHUNK * 9; i += CTA) (&s_g[0][0])[i] = 0.f;
-        mbar_wait(&s_bar[st], (uint32_t)((c / NSTAGE) & 1));
+#pragma unroll
+        for (int i = lane; i < CHUNK * 9; i += 32) (&s_g[warp][0][0])[i] = 0.f;  // own slice only
+        __syncwarp();
+        cp_async_wait<1>();
         __syncthreads();
         const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
         for (int j = 0; j < cnt; ++j) {
@@ -658,17 +696,19 @@ __global__ void __launch_bounds__(CTA) k_raster_bwd(const float* __restrict__ re
                     float v = gv[0];
 #pragma unroll
                     for (int k = 1; k < 9; ++k) v = (lane == k) ? gv[k] : v;
-                    atomicAdd(&s_g[j][lane], v);
+                    s_g[warp][j][lane] += v;
                 }
             }
         }
         __syncthreads();
         for (int i = tid; i < cnt * 9; i += CTA) {
             const int j = i / 9, k = i - j * 9;
-            const float v = s_g[j][k];
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) v += s_g[w][j][k];
             if (v != 0.f) atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
         }
-        if (warp == 0 && c + NSTAGE < nchunk) issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec, s_bar);
+        issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);
         __syncthreads();
     }
 }
@@ -715,9 +755,7 @@ static Consts make_consts(const UmrRasterParams* p) {
     return K;
 }
 
-static size_t raster_dyn_smem(int F) {
-    return (size_t)NSTAGE * CHUNK * REC_F * 4 + (((size_t)F * 2 + 15) & ~(size_t)15);
-}
+static size_t raster_dyn_smem(int F) { return smem_list_off(F) + (((size_t)F * 2 + 15) & ~(size_t)15); }
 
 extern "C" int umr_raster_forward(const float* face_vertices, const float* textures, float* images,
                                   float* soft_colors, float* aggrs_info, float* p2f_info,
