@@ -98,6 +98,35 @@ int umr_raster_backward(const float* face_vertices, const float* textures, const
                         float* grad_textures, const UmrRasterParams* params, void* workspace,
                         void* stream);
 
+/* Fused vertex pipeline: 7-dof orthographic camera projection with z
+ * (nnutils/geom_utils.py:74-91,119-165), y flip (nnutils/smr.py:36), look_at with the eye on the z axis
+ * + orthogonal scale (SoftRas/functional/look_at.py:48-60, orthogonal.py:13-16), the face gather
+ * (functional/face_vertices.py:16-22) and, optionally, the per-face surface light
+ * (SoftRas/lighting.py:50-57, mesh.py:112-118) in ONE kernel; bit-identical to the torch-op chain. */
+typedef struct UmrProjectParams {
+    int32_t batch_size, num_vertices, num_faces;
+    int32_t flip_y;              /* 1: y *= -1 after the projection (smr.py:36) */
+    int64_t faces_batch_stride;  /* elements between consecutive batches of `faces` (F*3, or 0 if shared) */
+    float offset_z;              /* smr.py:66 */
+    float eye_z;                 /* look_at eye = (0, 0, eye_z) (smr.py:60: -2.732) */
+    float viewing_scale;         /* orthogonal scale */
+    int32_t light_enabled;       /* 0: `light` is not written */
+    float light_intensity_ambient, light_intensity_directional;
+    float light_color_ambient[3], light_color_directional[3], light_direction[3];
+} UmrProjectParams;
+
+/* vertices [B,V,3] f32, cams [B,7] = [s,tx,ty,qw,qx,qy,qz], faces int32 -> face_vertices [B,F,9]
+ * (raster space) and light [B,F,3] (NULL or light_enabled == 0 to skip). */
+int umr_project_faces_forward(const float* vertices, const float* cams, const int32_t* faces,
+                              float* face_vertices, float* light, const UmrProjectParams* params,
+                              void* stream);
+/* grad_face_vertices [B,F,9] (+ grad_light [B,F,3] or NULL) -> grad_vertices [B,V,3] (NULL to skip),
+ * grad_cams [B,7] (NULL to skip).  grad_proj [B,V,3] is scratch (zero-filled by the call). */
+int umr_project_faces_backward(const float* vertices, const float* cams, const int32_t* faces,
+                               const float* grad_face_vertices, const float* grad_light, float* grad_proj,
+                               float* grad_vertices, float* grad_cams, const UmrProjectParams* params,
+                               void* stream);
+
 /* Bilinear sampler, align_corners=True, zeros padding (geom_utils.py:41-59, loss_utils.py:59-64).
  * image [B,C,H,W], flow [B,N,2] (x,y in [-1,1]) -> out [B,N,C] (i.e. already permuted to the
  * `B x F x T x T x C` order sample_textures returns).  Backward: gradient w.r.t. flow only

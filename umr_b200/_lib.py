@@ -25,6 +25,16 @@ class UmrRasterParams(ctypes.Structure):
                 ("ev_kernel_start", ctypes.c_void_p), ("ev_kernel_stop", ctypes.c_void_p)]
 
 
+class UmrProjectParams(ctypes.Structure):
+    _fields_ = [("batch_size", ctypes.c_int32), ("num_vertices", ctypes.c_int32), ("num_faces", ctypes.c_int32),
+                ("flip_y", ctypes.c_int32), ("faces_batch_stride", ctypes.c_int64),
+                ("offset_z", ctypes.c_float), ("eye_z", ctypes.c_float), ("viewing_scale", ctypes.c_float),
+                ("light_enabled", ctypes.c_int32),
+                ("light_intensity_ambient", ctypes.c_float), ("light_intensity_directional", ctypes.c_float),
+                ("light_color_ambient", ctypes.c_float * 3), ("light_color_directional", ctypes.c_float * 3),
+                ("light_direction", ctypes.c_float * 3)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "umr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
@@ -39,6 +49,8 @@ EXPORTS = {
                                                         ctypes.c_void_p]),
     "umr_raster_backward": (ctypes.c_int, [c_f32p] * 7 + [ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
                                                          ctypes.c_void_p]),
+    "umr_project_faces_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.POINTER(UmrProjectParams), ctypes.c_void_p]),
+    "umr_project_faces_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.POINTER(UmrProjectParams), ctypes.c_void_p]),
     "umr_bilinear_sample_forward": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),
     "umr_bilinear_sample_backward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),
     "umr_iou_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),

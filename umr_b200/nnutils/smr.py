@@ -8,6 +8,7 @@ and the same attribute paths the reference pokes (`renderer.transform.transforme
 import torch
 
 from .. import soft_renderer as sr
+from ..vertex import project_faces
 from . import geom_utils
 
 
@@ -48,7 +49,51 @@ class SoftRenderer(torch.nn.Module):
     def project_points(self, verts, cams):
         return self.proj_fn(verts, cams)[:, :, :2]
 
+    # -- fused path ---------------------------------------------------------------------------------
+    fuse_vertex_pipeline = True  # class-level switch (tests compare both paths)
+
+    def _fusable(self, vertices):
+        """The fused vertex kernel covers exactly the configuration this wrapper sets up (smr.py:56-66):
+        look_at camera with the eye on the z axis, orthographic, surface lighting with at most the one
+        default directional light.  Anything else takes the generic torch path below."""
+        r = self.renderer
+        tr = r.transform.transformer
+        eye = getattr(tr, "_eye", None)
+        if not (self.fuse_vertex_pipeline and vertices.is_cuda and r.transform.camera_mode == "look_at"
+                and not tr.perspective and isinstance(eye, (list, tuple)) and len(eye) == 3):
+            return False
+        if float(eye[0]) != 0.0 or float(eye[1]) != 0.0 or not float(eye[2]) < 0.0:
+            return False
+        if self.proj_fn is not geom_utils.orthographic_proj_withz or len(r.lighting.directionals) != 1:
+            return False
+        return r.rasterizer.texture_type == "surface"
+
+    def _forward_fused(self, vertices, faces, cams, textures):
+        r = self.renderer
+        tr = r.transform.transformer
+        amb, dl = r.lighting.ambient, r.lighting.directionals[0]
+        light_cfg = None
+        if float(dl.light_intensity) != 0.0:
+            light_cfg = (amb.light_intensity, amb.light_color, dl.light_intensity, dl.light_color, dl.light_direction)
+        fv, light = project_faces(vertices, cams, faces, offset_z=self.offset_z, eye_z=float(tr._eye[2]),
+                                  viewing_scale=tr.viewing_scale, flip_y=True, light=light_cfg)
+        B, F = fv.shape[:2]
+        if light is not None:
+            # ones * light == light; textures * light[:, :, None, :] as in lighting.py:57
+            tex = light[:, :, None, :] if textures is None else textures * light[:, :, None, :]
+        else:
+            c = [float(amb.light_intensity) * float(k) for k in amb.light_color]
+            if textures is None:
+                tex = torch.tensor(c, dtype=torch.float32, device=fv.device).view(1, 1, 1, 3).expand(B, F, 1, 3)
+            elif c == [1.0, 1.0, 1.0]:
+                tex = textures  # x * 1 == x
+            else:
+                tex = textures * torch.tensor(c, dtype=torch.float32, device=fv.device)
+        return r.rasterizer.rasterize(fv, tex)
+
     def forward(self, vertices, faces, cams, textures=None):
+        if self._fusable(vertices):
+            return self._forward_fused(vertices, faces, cams, textures)
         faces = faces.int()
         verts = self.proj_fn(vertices, cams, offset_z=self.offset_z)
         if textures is not None:

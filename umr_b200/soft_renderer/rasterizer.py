@@ -33,7 +33,12 @@ class SoftRasterizer(nn.Module):
         self.texture_type = texture_type
 
     def forward(self, mesh, mode=None):
-        return soft_rasterize(mesh.face_vertices, mesh.face_textures, self.image_size, self.background_color,
+        return self.rasterize(mesh.face_vertices, mesh.face_textures)
+
+    def rasterize(self, face_vertices, face_textures):
+        """Rasterise raster-space face vertices [B,F,3,3] with face textures [B,F,T2,3]."""
+        return soft_rasterize(face_vertices, face_textures, self.image_size, self.background_color,
                               self.near, self.far, self.fill_back, self.eps, self.sigma_val, self.dist_func,
                               self.dist_eps, self.gamma_val, self.aggr_func_rgb, self.aggr_func_alpha,
                               self.texture_type, self.anti_aliasing)
+
