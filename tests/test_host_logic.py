@@ -136,3 +136,27 @@ def test_shard_range_partitions():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_compat_install_and_overlay(tmp_path):
+    import importlib
+    import sys
+    from umr_b200 import compat
+    compat.install()
+    import soft_renderer as sr2
+    assert sr2.SoftRenderer is sr.SoftRenderer and hasattr(sr2, "LaplacianLoss") and hasattr(sr2.functional, "soft_rasterize")
+    # fake reference checkout
+    ref = tmp_path / "ref"
+    for d in ("experiments", "data", "utils", "nnutils"):
+        (ref / d).mkdir(parents=True)
+        (ref / d / "__init__.py").write_text("")
+    (ref / "nnutils" / "scops_utils.py").write_text("MARK = 'reference'\n")
+    (ref / "nnutils" / "smr.py").write_text("MARK = 'reference smr'\n")
+    base = compat.overlay(str(ref), package="UMRT", workdir=str(tmp_path / "ov"))
+    try:
+        m = importlib.import_module("UMRT.nnutils.smr")
+        assert m.SoftRenderer is smr.SoftRenderer            # ours
+        assert importlib.import_module("UMRT.nnutils.scops_utils").MARK == "reference"   # theirs, via symlink
+        assert importlib.import_module("UMRT.nnutils.chamfer_python").distChamfer is not None
+    finally:
+        sys.path.remove(base)
