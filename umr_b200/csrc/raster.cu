@@ -343,47 +343,76 @@ struct Consts {
 };
 
 // =============================================================================================
+// thread <-> pixel mapping: a warp covers an 8x4 pixel block (better lane utilisation against the
+// ~23x23-pixel cull boxes than a 16x2 strip: profiles/r01_*), a CTA a 16x16 tile = 2x4 warp blocks.
+// The 2x2 anti-aliasing quad of the (even x, even y) lane is lanes ^1, ^8, ^9.
+// =============================================================================================
+struct PixelMap {
+    int px, py;
+    bool live;
+    float xp, yp;
+};
+__device__ __forceinline__ PixelMap map_pixel(int S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PixelMap m;
+    m.px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+    m.py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);  // image row (0 = top)
+    m.live = m.px < S && m.py < S;
+    m.xp = pixel_coord(m.px, S);
+    m.yp = pixel_coord(S - 1 - m.py, S);
+    return m;
+}
+
+// tile extents in pixel-centre coordinates (monotone in the index, so the cull test is conservative);
+// four threads compute one division each and broadcast through shared memory
+__device__ __forceinline__ void tile_extents(int S, float* s_ext) {
+    const int t = threadIdx.x;
+    if (t < 4) {
+        const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
+        const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
+        const int i = t == 0 ? blockIdx.x * TILE : t == 1 ? x_last_i : t == 2 ? S - 1 - y_last_i : S - 1 - blockIdx.y * TILE;
+        s_ext[t] = pixel_coord(i, S);  // 0: x first, 1: x last, 2: y bottom, 3: y top
+    }
+}
+
+// =============================================================================================
 // forward
 // =============================================================================================
 template <int RGB>  // 1 softmax, 0 hard
 __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__ rec_all,
-                                                    const float4* __restrict__ box_all,
-                                                    const float* __restrict__ textures,
-                                                    float* __restrict__ images, float* __restrict__ colors_hi,
-                                                    float* __restrict__ aggrs, float* __restrict__ p2f_acc,
-                                                    Consts K, float eps, float bg0, float bg1, float bg2) {
+                                                       const float4* __restrict__ box_all,
+                                                       const float* __restrict__ textures,
+                                                       float* __restrict__ images, float* __restrict__ colors_hi,
+                                                       float* __restrict__ aggrs, float* __restrict__ p2f_acc,
+                                                       Consts K, float eps, float bg0, float bg1, float bg2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
     float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + smem_list_off(K.F));
     __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[NWARP];
-    __shared__ float s_p2f[NWARP][CHUNK][3];  // per-warp partial sums: no shared atomics
+    __shared__ float s_ext[4];
+    __shared__ float s_p2f[CHUNK][3];  // per-(tile, chunk face) p2f partial sums
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
     const int S = K.S, F = K.F;
-    // lane -> pixel: a warp covers a 16x2 strip so the 2x2 pool partners are lanes ^1 and ^16
-    const int px = blockIdx.x * TILE + (lane & 15);
-    const int py = blockIdx.y * TILE + warp * 2 + (lane >> 4);  // image row (0 = top)
-    const bool live = px < S && py < S;
-    const float xp = pixel_coord(px, S);
-    const float yp = pixel_coord(S - 1 - py, S);
+    const PixelMap pm = map_pixel(S);
+    const int px = pm.px, py = pm.py;
+    const bool live = pm.live;
+    const float xp = pm.xp, yp = pm.yp;
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
+    tile_extents(S, s_ext);
+    if (RGB == 1 && tid < CHUNK * 3) (&s_p2f[0][0])[tid] = 0.f;
     __syncthreads();
-    // tile extents in pixel-centre coordinates (monotone in the index, so the test is conservative)
-    const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
-    const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
-    const float tx_first = pixel_coord(blockIdx.x * TILE, S), tx_last = pixel_coord(x_last_i, S);
-    const float ty_top = pixel_coord(S - 1 - blockIdx.y * TILE, S), ty_bot = pixel_coord(S - 1 - y_last_i, S);
 
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_box, s_list, s_warp_cnt, &s_bar);
+    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
     // (build_tile_list ends with __syncthreads: the list is visible)
 
     // pixel state (kernel.cu:335-348)
@@ -410,17 +439,16 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % NSTAGE;
         const int cnt = min(CHUNK, n - c * CHUNK);
-        if (RGB == 1) {
-#pragma unroll
-            for (int i = lane; i < CHUNK * 3; i += 32) (&s_p2f[warp][0][0])[i] = 0.f;  // own slice only
-            __syncwarp();
-        }
         cp_async_wait<1>();  // chunk c has landed (c+1 may still be in flight)
-        __syncthreads();
+        __syncthreads();     // ... for every thread; also: s_p2f is zero again
         const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
+        // p2f partial sums of this warp: lane j owns chunk face j (registers, no shared traffic)
+        float own_x = 0.f, own_y = 0.f, own_w = 0.f;
+        float4 bb = *reinterpret_cast<const float4*>(chunk + R_BOX);
         for (int j = 0; j < cnt; ++j) {
             const float* rc = chunk + j * REC_F;
-            const float4 bb = *reinterpret_cast<const float4*>(rc + R_BOX);
+            // prefetch the next cull box while this face is evaluated
+            const float4 bbn = *reinterpret_cast<const float4*>(chunk + (j + 1 < cnt ? j + 1 : j) * REC_F + R_BOX);
             float a_x = 0.f, a_y = 0.f, a_w = 0.f;
             bool contrib = false;
             if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
@@ -460,29 +488,31 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
                     }
                 }
             }
-            if (RGB == 1) {
-                // p2f: warp-shuffle reduction, one shared atomic per warp (replaces the 4 global
-                // atomics per (pixel, face) of kernel.cu:427-430)
+            if (RGB == 1 && p2f_acc != nullptr) {
+                // p2f: warp-shuffle reduction (replaces the 4 global atomics per (pixel, face) of
+                // kernel.cu:427-430); the totals stay in the registers of lane j
                 if (__any_sync(0xffffffffu, contrib)) {
                     a_x = warp_sum(a_x); a_y = warp_sum(a_y); a_w = warp_sum(a_w);
-                    if (lane == 0) {
-                        s_p2f[warp][j][0] += a_x;
-                        s_p2f[warp][j][1] += a_y;
-                        s_p2f[warp][j][2] += a_w;
-                    }
+                    if (lane == j) { own_x += a_x; own_y += a_y; own_w += a_w; }
                 }
             }
+            bb = bbn;
         }
-        __syncthreads();  // everyone is done with stage st (and s_p2f is complete)
-        if (RGB == 1 && p2f_acc != nullptr && tid < cnt * 3) {
+        if (RGB == 1 && p2f_acc != nullptr && own_w != 0.f) {  // one shared atomic per (warp, face)
+            atomicAdd(&s_p2f[lane][0], own_x);
+            atomicAdd(&s_p2f[lane][1], own_y);
+            atomicAdd(&s_p2f[lane][2], own_w);
+        }
+        __syncthreads();  // everyone is done with stage st; s_p2f is complete
+        if (RGB == 1 && p2f_acc != nullptr && tid < cnt * 3) {  // one global atomic per (tile, face)
             const int j = tid / 3, k = tid - j * 3;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < NWARP; ++w) v += s_p2f[w][j][k];
-            if (v != 0.f) atomicAdd(p2f_acc + ((size_t)b * F + s_list[c * CHUNK + j]) * 4 + k, v);
+            const float v = s_p2f[j][k];
+            if (v != 0.f) {
+                atomicAdd(p2f_acc + ((size_t)b * F + s_list[c * CHUNK + j]) * 4 + k, v);
+                s_p2f[j][k] = 0.f;
+            }
         }
         issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);  // commits an empty group past the end
-        if (RGB == 1) __syncthreads();  // s_p2f flushed before the next chunk zeroes it
     }
 
     // finalise (kernel.cu:443-475)
@@ -492,7 +522,10 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
         o0 = c0; o1 = c1; o2 = c2;  // background kept when no face won (c* still bg)
         g0 = zmin; g1 = (float)fid;
     } else {
-        o0 = c0 / ssum; o1 = c1 / ssum; o2 = c2 / ssum;
+        // 0 / ssum == 0 exactly: skip the IEEE division for black-background / untouched pixels
+        o0 = c0 == 0.f ? c0 : c0 / ssum;
+        o1 = c1 == 0.f ? c1 : c1 / ssum;
+        o2 = c2 == 0.f ? c2 : c2 / ssum;
         g0 = ssum; g1 = smax;
     }
     const size_t np = (size_t)S * S;
@@ -510,14 +543,19 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
     if (K.aa) {
         // avg_pool2d(2,2): ((a00 + a01) + a10) + a11, then /4 (rasterizer.py:52-53)
         float v[4] = {o0, o1, o2, alpha};
+        if (n > 0) {  // uniform
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float a01 = __shfl_xor_sync(0xffffffffu, v[k], 1);
-            const float a10 = __shfl_xor_sync(0xffffffffu, v[k], 16);
-            const float a11 = __shfl_xor_sync(0xffffffffu, v[k], 17);
-            v[k] = (((v[k] + a01) + a10) + a11) * 0.25f;  // meaningful on the (even x, even y) lane
+            for (int k = 0; k < 4; ++k) {
+                const float a01 = __shfl_xor_sync(0xffffffffu, v[k], 1);
+                const float a10 = __shfl_xor_sync(0xffffffffu, v[k], 8);
+                const float a11 = __shfl_xor_sync(0xffffffffu, v[k], 9);
+                v[k] = (((v[k] + a01) + a10) + a11) * 0.25f;  // meaningful on the (even x, even y) lane
+            }
+        } else {  // untouched tile: the quad holds four identical values; same arithmetic, no shuffles
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (((v[k] + v[k]) + v[k]) + v[k]) * 0.25f;
         }
-        if (live && (lane & 1) == 0 && (lane & 16) == 0) {
+        if (live && (lane & 1) == 0 && (lane & 8) == 0) {
             const int IS = K.IS;
             const size_t q = (size_t)(py >> 1) * IS + (px >> 1);
             const size_t nq = (size_t)IS * IS;
@@ -546,42 +584,40 @@ __global__ void k_p2f_finalize(const float* __restrict__ acc, float* __restrict_
 // =============================================================================================
 template <int RGB, bool TEXGRAD>
 __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__ rec_all,
-                                                    const float4* __restrict__ box_all,
-                                                    const float* __restrict__ textures,
-                                                    const float* __restrict__ colors_hi,
-                                                    const float* __restrict__ aggrs,
-                                                    const float* __restrict__ grad_images,
-                                                    float* __restrict__ grad_faces, float* __restrict__ grad_tex,
-                                                    Consts K) {
+                                                       const float4* __restrict__ box_all,
+                                                       const float* __restrict__ textures,
+                                                       const float* __restrict__ colors_hi,
+                                                       const float* __restrict__ aggrs,
+                                                       const float* __restrict__ grad_images,
+                                                       float* __restrict__ grad_faces, float* __restrict__ grad_tex,
+                                                       Consts K) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
     float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + smem_list_off(K.F));
     __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[NWARP];
-    __shared__ float s_g[NWARP][CHUNK][9];  // per-warp partial gradients: no shared atomics
+    __shared__ float s_ext[4];
+    __shared__ float s_g[CHUNK][9];  // per-(tile, chunk face) vertex-gradient partial sums
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
     const int S = K.S, F = K.F;
-    const int px = blockIdx.x * TILE + (lane & 15);
-    const int py = blockIdx.y * TILE + warp * 2 + (lane >> 4);
-    const bool live = px < S && py < S;
-    const float xp = pixel_coord(px, S);
-    const float yp = pixel_coord(S - 1 - py, S);
+    const PixelMap pm = map_pixel(S);
+    const int px = pm.px, py = pm.py;
+    const bool live = pm.live;
+    const float xp = pm.xp, yp = pm.yp;
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
+    tile_extents(S, s_ext);
+    for (int i = tid; i < CHUNK * 9; i += CTA) (&s_g[0][0])[i] = 0.f;
     __syncthreads();
-    const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
-    const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
-    const float tx_first = pixel_coord(blockIdx.x * TILE, S), tx_last = pixel_coord(x_last_i, S);
-    const float ty_top = pixel_coord(S - 1 - blockIdx.y * TILE, S), ty_bot = pixel_coord(S - 1 - y_last_i, S);
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const int n = build_tile_list(box, F, tx_first, tx_last, ty_bot, ty_top, s_box, s_list, s_warp_cnt, &s_bar);
+    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
     if (n == 0) return;  // uniform
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
@@ -619,15 +655,17 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % NSTAGE;
         const int cnt = min(CHUNK, n - c * CHUNK);
-#pragma unroll
-        for (int i = lane; i < CHUNK * 9; i += 32) (&s_g[warp][0][0])[i] = 0.f;  // own slice only
-        __syncwarp();
         cp_async_wait<1>();
-        __syncthreads();
+        __syncthreads();  // chunk c visible to all; s_g is zero again
         const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
+        float own[9];  // vertex-gradient partial sums of this warp: lane j owns chunk face j
+#pragma unroll
+        for (int k = 0; k < 9; ++k) own[k] = 0.f;
+        bool own_any = false;
+        float4 bb = *reinterpret_cast<const float4*>(chunk + R_BOX);
         for (int j = 0; j < cnt; ++j) {
             const float* rc = chunk + j * REC_F;
-            const float4 bb = *reinterpret_cast<const float4*>(rc + R_BOX);
+            const float4 bbn = *reinterpret_cast<const float4*>(chunk + (j + 1 < cnt ? j + 1 : j) * REC_F + R_BOX);
             float gv[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) gv[k] = 0.f;
@@ -689,27 +727,33 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
                     }
                 }
             }
+            // 9 vertex gradients: warp-shuffle reduction instead of the reference's 9 global atomics per
+            // (pixel, face) (kernel.cu:645-654); totals stay in the registers of lane j
             if (__any_sync(0xffffffffu, contrib)) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) gv[k] = warp_sum(gv[k]);
-                if (lane < 9) {
-                    float v = gv[0];
+                if (lane == j) {
 #pragma unroll
-                    for (int k = 1; k < 9; ++k) v = (lane == k) ? gv[k] : v;
-                    s_g[warp][j][lane] += v;
+                    for (int k = 0; k < 9; ++k) own[k] += gv[k];
+                    own_any = true;
                 }
             }
+            bb = bbn;
         }
-        __syncthreads();
-        for (int i = tid; i < cnt * 9; i += CTA) {
-            const int j = i / 9, k = i - j * 9;
-            float v = 0.f;
+        if (own_any) {  // one shared atomic per (warp, face, component)
 #pragma unroll
-            for (int w = 0; w < NWARP; ++w) v += s_g[w][j][k];
-            if (v != 0.f) atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
+            for (int k = 0; k < 9; ++k) atomicAdd(&s_g[lane][k], own[k]);
+        }
+        __syncthreads();  // everyone is done with stage st; s_g is complete
+        for (int i = tid; i < cnt * 9; i += CTA) {  // one global atomic per (tile, face, component)
+            const float v = (&s_g[0][0])[i];
+            if (v != 0.f) {
+                const int j = i / 9, k = i - j * 9;
+                atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
+                (&s_g[0][0])[i] = 0.f;
+            }
         }
         issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);
-        __syncthreads();
     }
 }
 
