@@ -46,7 +46,7 @@ constexpr int R_FLG = 28;  // 1 : bit0..2 obtuse corner, bit3 front-facing
 // 29..31 pad
 
 struct WorkspaceLayout {
-    size_t rec_off, box_off, p2f_off, total;
+    size_t rec_off, box_off, p2f_off, ubox_off, total;
 };
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline WorkspaceLayout ws_layout(int B, int F) {
@@ -55,17 +55,29 @@ inline WorkspaceLayout ws_layout(int B, int F) {
     L.rec_off = 0;
     L.box_off = align256(n * REC_F * sizeof(float));
     L.p2f_off = L.box_off + align256(n * sizeof(float4));
-    L.total = L.p2f_off + align256(n * 4 * sizeof(float));
+    L.ubox_off = L.p2f_off + align256(n * 4 * sizeof(float));
+    L.total = L.ubox_off + align256((size_t)B * 4 * sizeof(uint32_t));
     return L;
 }
 
 // ---------------------------------------------------------------------------------------------
 // prep: kernel.cu:222-282 + the per-face parts of :32-44
 // ---------------------------------------------------------------------------------------------
+// Monotone key of a cull-box bound for atomicMax on a zero-initialised word: positive floats order like
+// their bit patterns; non-positive values map to 0 (the union box then merely contains the screen
+// centre, which stays conservative); NaN poisons the union so nothing is ever skipped.
+__device__ __forceinline__ uint32_t ubox_key(float v) {
+    if (v != v) return 0xffffffffu;
+    return v > 0.f ? __float_as_uint(v) : 0u;
+}
+
+// grid (ceil(F/256), B): every block belongs to one image.  Also accumulates the image's UNION cull box
+// ubox[b] = {max xhi, max -xlo, max yhi, max -ylo} (keys) so tiles outside it skip the face scan.
 __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ fv, float* __restrict__ rec,
-                                              float4* __restrict__ box, int n, float r) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                              float4* __restrict__ box, uint32_t* __restrict__ ubox, int F, float r) {
+    const int fidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = fidx < F;
+    const int i = blockIdx.y * F + (valid ? fidx : F - 1);  // clamp: the tail threads redo the last face
     const float* f = fv + (size_t)i * 9;
     float v[9];
 #pragma unroll
@@ -102,11 +114,35 @@ __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ fv, floa
     if ((y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0)) flags |= 8;  // kernel.cu:42-44
     out[R_FLG] = __uint_as_float(flags);
     out[29] = out[30] = out[31] = 0.f;
-    float4* dst = reinterpret_cast<float4*>(rec + (size_t)i * REC_F);
+    if (valid) {
+        float4* dst = reinterpret_cast<float4*>(rec + (size_t)i * REC_F);
 #pragma unroll
-    for (int k = 0; k < REC_F / 4; ++k)
-        dst[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
-    box[i] = make_float4(xlo, xhi, ylo, yhi);
+        for (int k = 0; k < REC_F / 4; ++k)
+            dst[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+        box[i] = make_float4(xlo, xhi, ylo, yhi);
+    }
+    // union box: warp max of the 4 keys, then one atomicMax per warp and bound
+    uint32_t k0 = ubox_key(xhi), k1 = ubox_key(-xlo), k2 = ubox_key(yhi), k3 = ubox_key(-ylo);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k0 = max(k0, __shfl_xor_sync(0xffffffffu, k0, o));
+        k1 = max(k1, __shfl_xor_sync(0xffffffffu, k1, o));
+        k2 = max(k2, __shfl_xor_sync(0xffffffffu, k2, o));
+        k3 = max(k3, __shfl_xor_sync(0xffffffffu, k3, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t* u = ubox + (size_t)blockIdx.y * 4;
+        atomicMax(u + 0, k0); atomicMax(u + 1, k1); atomicMax(u + 2, k2); atomicMax(u + 3, k3);
+    }
+}
+
+// true when the tile (pixel-centre extents in s_ext) lies completely outside the image's union cull box
+__device__ __forceinline__ bool tile_outside_union(const uint32_t* __restrict__ ubox, int b, const float* s_ext) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ubox) + b);
+    if (u.x == 0xffffffffu || u.y == 0xffffffffu || u.z == 0xffffffffu || u.w == 0xffffffffu) return false;  // NaN seen
+    const float xhi = __uint_as_float(u.x), xlo = -__uint_as_float(u.y);
+    const float yhi = __uint_as_float(u.z), ylo = -__uint_as_float(u.w);
+    return s_ext[0] > xhi || s_ext[1] < xlo || s_ext[2] > yhi || s_ext[3] < ylo;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,7 +420,8 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
                                                        const float* __restrict__ textures,
                                                        float* __restrict__ images, float* __restrict__ colors_hi,
                                                        float* __restrict__ aggrs, float* __restrict__ p2f_acc,
-                                                       Consts K, float eps, float bg0, float bg1, float bg2) {
+                                                       const uint32_t* __restrict__ ubox, Consts K, float eps,
+                                                       float bg0, float bg1, float bg2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
     float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
@@ -412,7 +449,9 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
 
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
+    const int n = tile_outside_union(ubox, b, s_ext)
+                      ? 0
+                      : build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
     // (build_tile_list ends with __syncthreads: the list is visible)
 
     // pixel state (kernel.cu:335-348)
@@ -590,7 +629,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
                                                        const float* __restrict__ aggrs,
                                                        const float* __restrict__ grad_images,
                                                        float* __restrict__ grad_faces, float* __restrict__ grad_tex,
-                                                       Consts K) {
+                                                       const uint32_t* __restrict__ ubox, Consts K) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
     float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
@@ -617,6 +656,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
     __syncthreads();
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
+    if (tile_outside_union(ubox, b, s_ext)) return;  // uniform
     const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
     if (n == 0) return;  // uniform
 
@@ -817,9 +857,14 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     float* rec = (float*)(ws + L.rec_off);
     float4* box = (float4*)(ws + L.box_off);
     float* p2f_acc = (float*)(ws + L.p2f_off);
+    uint32_t* ubox = (uint32_t*)(ws + L.ubox_off);
     const int n = B * F;
     const float r = sqrtf(K.thr);  // kernel.cu:355 sqrt(threshold) in float
-    k_prep<<<(n + 255) / 256, 256, 0, stream>>>(face_vertices, rec, box, n, r);
+    {
+        cudaError_t e0 = cudaMemsetAsync(ubox, 0, (size_t)B * 4 * sizeof(uint32_t), stream);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
+    k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, r);
     count_launch();
     const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
     const bool want_p2f = p2f_info != nullptr;
@@ -835,14 +880,14 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(k_raster_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_raster_fwd<1><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
-                                                     want_p2f ? p2f_acc : nullptr, K, p->eps,
+                                                     want_p2f ? p2f_acc : nullptr, ubox, K, p->eps,
                                                      p->background_color[0], p->background_color[1],
                                                      p->background_color[2]);
     } else {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(k_raster_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_raster_fwd<0><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
-                                                     nullptr, K, p->eps, p->background_color[0],
+                                                     nullptr, ubox, K, p->eps, p->background_color[0],
                                                      p->background_color[1], p->background_color[2]);
     }
     if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
@@ -875,12 +920,15 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     char* ws = (char*)workspace;
     float* rec = (float*)(ws + L.rec_off);
     float4* box = (float4*)(ws + L.box_off);
+    uint32_t* ubox = (uint32_t*)(ws + L.ubox_off);
     const int n = B * F;
     const float r = sqrtf(K.thr);
     // the workspace is scratch (another render may have used it since forward): rebuild the records
-    k_prep<<<(n + 255) / 256, 256, 0, stream>>>(face_vertices, rec, box, n, r);
+    cudaError_t e = cudaMemsetAsync(ubox, 0, (size_t)B * 4 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return (int)e;
+    k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, r);
     count_launch();
-    cudaError_t e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
+    e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
     if (e != cudaSuccess) return (int)e;
     if (grad_textures) {
         e = cudaMemsetAsync(grad_textures, 0, (size_t)n * p->texture_size * 3 * sizeof(float), stream);
@@ -895,7 +943,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
             cudaFuncSetAttribute(k_raster_bwd<RGBM, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)smem);                                                            \
         k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
-                                                            grad_images, grad_faces, grad_textures, K); \
+                                                            grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();
