@@ -230,6 +230,26 @@ class Workload:
         loss = self.step(self.stage, world)
         return float(loss.item())                    # D2H read of the step's result
 
+    # ---- CUDA-graph variants: the same step(), captured once per static input buffer set ----------
+    def capture(self, world):
+        from umr_b200.graph import GraphedStep
+        self.g_res = []
+        pool = None
+        for i in range(NUM_SETS):
+            g = GraphedStep(lambda i=i: self.step(self.dev[i], world), warmup=2 if i == 0 else 1, pool=pool)
+            pool = g.pool()
+            self.g_res.append(g)
+        self.g_e2e = GraphedStep(lambda: self.step(self.stage, world), warmup=1, pool=pool)
+
+    def gstep_resident(self, i, world):
+        return self.g_res[i % NUM_SETS]()
+
+    def gstep_e2e(self, i, world):
+        h = self.host[i % NUM_SETS]
+        for s, t in zip(self.stage, h):
+            s.copy_(t, non_blocking=True)
+        return float(self.g_e2e().item())
+
 
 def run_gpu(args, cfg):
     import torch
@@ -282,9 +302,17 @@ def run_gpu(args, cfg):
             ms = float(t.item())
         return ms, launches, clocks, sink
 
-    ms_res, launches, clocks, sink = timed(wl.step_resident, profile=True)
+    use_graph = not args.no_graph
+    # eager pass: also records the raster kernels' own durations through the C-ABI event hooks
+    ms_eager, launches, clocks_eager, sink = timed(wl.step_resident, profile=True)
     kern = raster.collect_profile(sink)  # {"fwd": [ms...], "bwd": [ms...]}
-    ms_e2e, _, clocks_e2e, _ = timed(wl.step_e2e)
+    if use_graph:
+        wl.capture(world)
+        ms_res, _, clocks, _ = timed(wl.gstep_resident)
+        ms_e2e, _, clocks_e2e, _ = timed(wl.gstep_e2e)
+    else:
+        ms_res, clocks = ms_eager, clocks_eager
+        ms_e2e, _, clocks_e2e, _ = timed(wl.step_e2e)
 
     B = cfg["batch"]
     total_images = B * world * K
@@ -307,7 +335,8 @@ def run_gpu(args, cfg):
                    "image_size": cfg["image_size"], "raster_size": 2 * cfg["image_size"], "faces": wl.F,
                    "vertices": wl.V, "texture_res": cfg["tex_res"], "parallelism": "dp%d" % world,
                    "l2": "inputs rotate over %d pre-generated batches (> 126 MB L2 together with the per-step "
-                         "buffers)" % NUM_SETS},
+                         "buffers)" % NUM_SETS,
+                   "cuda_graph": use_graph, "eager_ms_per_step": ms_eager / K},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
@@ -315,6 +344,8 @@ def run_gpu(args, cfg):
         "roofline": {"bound": "hbm", "kernel": "k_raster_bwd<softmax,texgrad>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": peak_src, "kernel_ms": bwd_ms,
+                     "timing": "CUDA events recorded by the C ABI around the kernel launch, %d eager steps of the same "
+                               "workload inside this run" % K,
                      "alg_bytes_per_launch": bwd_b * B,
                      "fwd_kernel": {"kernel": "k_raster_fwd<softmax>", "kernel_ms": fwd_ms,
                                     "achieved": fwd_achieved, "frac": fwd_achieved / peak if peak else None,
@@ -363,6 +394,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of its CUDA-graph replay")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config], name=args.config)
     if args.impl == "reference":

@@ -139,12 +139,26 @@ int umr_bilinear_sample_backward(const float* image, const float* flow, const fl
                                  int32_t H, int32_t W, int32_t N, void* stream);
 
 /* neg_iou_loss (loss_utils.py:41-48).  predict/target [B,N] -> inter[B], uni[B] (uni includes the
- * +1e-6) and loss[B] = 1 - inter/uni.  Backward: grad_predict[B,N] = grad_loss[b] * dloss/dp. */
-int umr_iou_forward(const float* predict, const float* target, float* inter, float* uni,
-                    float* loss, int32_t B, int64_t N, void* stream);
+ * +1e-6) and loss[B] = 1 - inter/uni.  `predict` may be a strided view (e.g. the alpha plane of the
+ * RGBA render): predict_bstride = elements between batch items (N when contiguous).
+ * Backward: grad_predict[B,N] (contiguous) = grad_loss[b] * dloss/dp. */
+int umr_iou_forward(const float* predict, int64_t predict_bstride, const float* target, float* inter,
+                    float* uni, float* loss, int32_t B, int64_t N, void* stream);
 int umr_iou_backward(const float* target, const float* inter, const float* uni,
                      const float* grad_loss, float* grad_predict, int32_t B, int64_t N,
                      void* stream);
+
+/* texture_loss_masks (loss_utils.py:103-116): per image mean |pred*mask_pred - gt*mask_gt| over C*H*W.
+ * pred [B,C,HW] and mask_pred [B,HW] may be strided views of the RGBA render: their batch strides (in
+ * elements) are passed; gt [B,C,HW], mask_gt [B,HW] contiguous.  loss [B] (zero-filled by the call).
+ * Backward: grad_pred [B,C,HW], grad_mask_pred [B,HW] (contiguous, fully written; either may be NULL). */
+int umr_masked_l1_forward(const float* pred, int64_t pred_bstride, const float* mask_pred,
+                          int64_t mask_pred_bstride, const float* gt, const float* mask_gt, float* loss,
+                          int32_t B, int32_t C, int64_t HW, void* stream);
+int umr_masked_l1_backward(const float* pred, int64_t pred_bstride, const float* mask_pred,
+                           int64_t mask_pred_bstride, const float* gt, const float* mask_gt,
+                           const float* grad_loss, float* grad_pred, float* grad_mask_pred, int32_t B,
+                           int32_t C, int64_t HW, void* stream);
 
 /* distChamfer (chamfer_python.py:43-64) for D == 2 or 3.  a [B,N,D], b [B,M,D] ->
  * dist_ab[B,N], dist_ba[B,M], idx_ab[B,N] (int32), idx_ba[B,M] (int32), using the reference's

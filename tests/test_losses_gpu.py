@@ -123,3 +123,21 @@ def test_tex_cycle():
 def test_ops_reject_cpu():
     with pytest.raises(TypeError):
         ops.bilinear_sample(torch.zeros(1, 1, 4, 4), torch.zeros(1, 3, 2))
+
+
+@pytest.mark.parametrize("avg", [False, True])
+def test_texture_loss_masks_fused(avg):
+    g = torch.Generator().manual_seed(5)
+    B, H = 3, 40
+    rgba = torch.rand(B, 4, H, H, generator=g)
+    gt = torch.rand(B, 3, H, H, generator=g)
+    mgt = (torch.rand(B, H, H, generator=g) > 0.4).float()
+    r = rgba.clone().requires_grad_(True)
+    ref = oracle.texture_loss_masks(r[:, :3], gt, mgt, r[:, 3], avg=avg)
+    w = torch.rand(ref.shape, generator=g) if not avg else torch.tensor(1.0)
+    (ref * w).sum().backward()
+    x = rgba.to(DEV).requires_grad_(True)
+    got = loss_utils.texture_loss_masks(x[:, :3], gt.to(DEV), mgt.to(DEV), x[:, 3], avg=avg)  # strided views
+    (got * w.to(DEV)).sum().backward()
+    _chk("masked l1", got, ref)
+    _chk("masked l1 drgba", x.grad, r.grad, 1e-4, 1e-9)

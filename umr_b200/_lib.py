@@ -53,8 +53,14 @@ EXPORTS = {
     "umr_project_faces_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.POINTER(UmrProjectParams), ctypes.c_void_p]),
     "umr_bilinear_sample_forward": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),
     "umr_bilinear_sample_backward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),
-    "umr_iou_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "umr_iou_forward": (ctypes.c_int, [c_f32p, ctypes.c_int64] + [c_f32p] * 4 + [ctypes.c_int32, ctypes.c_int64,
+                                                                                  ctypes.c_void_p]),
     "umr_iou_backward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "umr_masked_l1_forward": (ctypes.c_int, [c_f32p, ctypes.c_int64, c_f32p, ctypes.c_int64, c_f32p, c_f32p, c_f32p,
+                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "umr_masked_l1_backward": (ctypes.c_int, [c_f32p, ctypes.c_int64, c_f32p, ctypes.c_int64, c_f32p, c_f32p, c_f32p,
+                                              c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                              ctypes.c_void_p]),
     "umr_chamfer_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
     "umr_chamfer_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
     "umr_texcycle_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_int64,

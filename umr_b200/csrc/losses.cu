@@ -95,9 +95,9 @@ constexpr int IOU_PER_CTA = IOU_THREADS * 4 * 8;  // elements per CTA
 
 __global__ void __launch_bounds__(IOU_THREADS) k_iou_partial(const float* __restrict__ p, const float* __restrict__ t,
                                                              float* __restrict__ inter, float* __restrict__ uni,
-                                                             int64_t N) {
+                                                             int64_t N, int64_t p_bstride) {
     const int b = blockIdx.y;
-    const float* pb = p + (size_t)b * N;
+    const float* pb = p + (size_t)b * p_bstride;
     const float* tb = t + (size_t)b * N;
     const int64_t begin = (int64_t)blockIdx.x * IOU_PER_CTA;
     const int64_t end = min(N, begin + IOU_PER_CTA);
@@ -267,6 +267,72 @@ __global__ void __launch_bounds__(256) k_texcycle_bwd(const float2* __restrict__
     for (int t = 0; t < T2; ++t) gflow[(size_t)i * T2 + t] = make_float2(gx, gy);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// masked L1 texture loss: nnutils/loss_utils.py:103-116 `texture_loss_masks`
+//   per image: sum_{c,h,w} | pred[c]*mask_pred - gt[c]*mask_gt | / (C*H*W)
+// pred / mask_pred may be strided views of the renderer's RGBA output (batch strides passed in).
+// ---------------------------------------------------------------------------------------------
+constexpr int ML1_THREADS = 256;
+constexpr int ML1_PER_CTA = ML1_THREADS * 8;  // pixels per CTA
+
+template <int C>
+__global__ void __launch_bounds__(ML1_THREADS) k_masked_l1_fwd(const float* __restrict__ pred, int64_t pred_bs,
+                                                              const float* __restrict__ mpred, int64_t mpred_bs,
+                                                              const float* __restrict__ gt, const float* __restrict__ mgt,
+                                                              float* __restrict__ loss, int64_t HW, float inv_n) {
+    const int b = blockIdx.y;
+    const float* p = pred + (size_t)b * pred_bs;
+    const float* mp = mpred + (size_t)b * mpred_bs;
+    const float* g = gt + (size_t)b * C * HW;
+    const float* mg = mgt + (size_t)b * HW;
+    const int64_t begin = (int64_t)blockIdx.x * ML1_PER_CTA;
+    const int64_t end = min(HW, begin + ML1_PER_CTA);
+    float acc = 0.f;
+    for (int64_t i = begin + threadIdx.x; i < end; i += ML1_THREADS) {
+        const float a = __ldg(mp + i), m = __ldg(mg + i);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc += fabsf(__ldg(p + (size_t)c * HW + i) * a - __ldg(g + (size_t)c * HW + i) * m);
+    }
+    acc = warp_sum(acc);
+    __shared__ float s[ML1_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < ML1_THREADS / 32 ? s[lane] : 0.f;
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(loss + b, acc * inv_n);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(ML1_THREADS) k_masked_l1_bwd(const float* __restrict__ pred, int64_t pred_bs,
+                                                              const float* __restrict__ mpred, int64_t mpred_bs,
+                                                              const float* __restrict__ gt, const float* __restrict__ mgt,
+                                                              const float* __restrict__ gl, float* __restrict__ gpred,
+                                                              float* __restrict__ gmask, int64_t HW, float inv_n) {
+    const int b = blockIdx.y;
+    const float* p = pred + (size_t)b * pred_bs;
+    const float* mp = mpred + (size_t)b * mpred_bs;
+    const float* g = gt + (size_t)b * C * HW;
+    const float* mg = mgt + (size_t)b * HW;
+    const float k = __ldg(gl + b) * inv_n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = __ldg(mp + i), m = __ldg(mg + i);
+        float gm = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float pv = __ldg(p + (size_t)c * HW + i);
+            const float d = pv * a - __ldg(g + (size_t)c * HW + i) * m;
+            const float sg = d > 0.f ? k : (d < 0.f ? -k : 0.f);  // torch: grad * sign(d), sign(0) = 0
+            if (gpred) gpred[((size_t)b * C + c) * HW + i] = sg * a;
+            gm += sg * pv;
+        }
+        if (gmask) gmask[(size_t)b * HW + i] = gm;
+    }
+}
+
 }  // namespace umr
 
 using namespace umr;
@@ -316,8 +382,8 @@ extern "C" int umr_bilinear_sample_backward(const float* image, const float* flo
     UMR_RET_LAST();
 }
 
-extern "C" int umr_iou_forward(const float* predict, const float* target, float* inter, float* uni, float* loss,
-                               int32_t B, int64_t N, void* stream_) {
+extern "C" int umr_iou_forward(const float* predict, int64_t predict_bstride, const float* target, float* inter,
+                               float* uni, float* loss, int32_t B, int64_t N, void* stream_) {
     if (!predict || !target || !inter || !uni || !loss || B <= 0 || N <= 0) return UMR_ERR_BAD_ARG;
     if (B > 65535) return UMR_ERR_TOO_LARGE;
     cudaStream_t st = (cudaStream_t)stream_;
@@ -326,7 +392,7 @@ extern "C" int umr_iou_forward(const float* predict, const float* target, float*
     e = cudaMemsetAsync(uni, 0, (size_t)B * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     const dim3 grid((unsigned)((N + IOU_PER_CTA - 1) / IOU_PER_CTA), B);
-    count_launch(); k_iou_partial<<<grid, IOU_THREADS, 0, st>>>(predict, target, inter, uni, N);
+    count_launch(); k_iou_partial<<<grid, IOU_THREADS, 0, st>>>(predict, target, inter, uni, N, predict_bstride);
     count_launch(); k_iou_finalize<<<(B + 127) / 128, 128, 0, st>>>(inter, uni, loss, B);
     UMR_RET_LAST();
 }
@@ -414,5 +480,39 @@ extern "C" int umr_texcycle_backward(const float* flow, const float* prob, const
     count_launch(); k_texcycle_bwd<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(flow),
                                                     reinterpret_cast<const float2*>(prob), visible, grad_loss,
                                                     reinterpret_cast<float2*>(grad_flow), n, T2, scale);
+    UMR_RET_LAST();
+}
+
+extern "C" int umr_masked_l1_forward(const float* pred, int64_t pred_bstride, const float* mask_pred,
+                                     int64_t mask_pred_bstride, const float* gt, const float* mask_gt, float* loss,
+                                     int32_t B, int32_t C, int64_t HW, void* stream_) {
+    if (!pred || !mask_pred || !gt || !mask_gt || !loss || B <= 0 || HW <= 0) return UMR_ERR_BAD_ARG;
+    if (B > 65535) return UMR_ERR_TOO_LARGE;
+    if (C != 3 && C != 1) return UMR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream_;
+    cudaError_t e = cudaMemsetAsync(loss, 0, (size_t)B * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    const dim3 grid((unsigned)((HW + ML1_PER_CTA - 1) / ML1_PER_CTA), B);
+    const float inv_n = 1.f / ((float)C * (float)HW);
+    count_launch();
+    if (C == 3) k_masked_l1_fwd<3><<<grid, ML1_THREADS, 0, st>>>(pred, pred_bstride, mask_pred, mask_pred_bstride, gt, mask_gt, loss, HW, inv_n);
+    else k_masked_l1_fwd<1><<<grid, ML1_THREADS, 0, st>>>(pred, pred_bstride, mask_pred, mask_pred_bstride, gt, mask_gt, loss, HW, inv_n);
+    UMR_RET_LAST();
+}
+
+extern "C" int umr_masked_l1_backward(const float* pred, int64_t pred_bstride, const float* mask_pred,
+                                      int64_t mask_pred_bstride, const float* gt, const float* mask_gt,
+                                      const float* grad_loss, float* grad_pred, float* grad_mask_pred, int32_t B,
+                                      int32_t C, int64_t HW, void* stream_) {
+    if (!pred || !mask_pred || !gt || !mask_gt || !grad_loss || B <= 0 || HW <= 0) return UMR_ERR_BAD_ARG;
+    if (B > 65535) return UMR_ERR_TOO_LARGE;
+    if (C != 3 && C != 1) return UMR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int64_t blocks = (HW + 256 * 4 - 1) / (256 * 4);
+    const dim3 grid((unsigned)(blocks < 1 ? 1 : (blocks > 1024 ? 1024 : blocks)), B);
+    const float inv_n = 1.f / ((float)C * (float)HW);
+    count_launch();
+    if (C == 3) k_masked_l1_bwd<3><<<grid, 256, 0, st>>>(pred, pred_bstride, mask_pred, mask_pred_bstride, gt, mask_gt, grad_loss, grad_pred, grad_mask_pred, HW, inv_n);
+    else k_masked_l1_bwd<1><<<grid, 256, 0, st>>>(pred, pred_bstride, mask_pred, mask_pred_bstride, gt, mask_gt, grad_loss, grad_pred, grad_mask_pred, HW, inv_n);
     UMR_RET_LAST();
 }

@@ -839,6 +839,26 @@ static Consts make_consts(const UmrRasterParams* p) {
     return K;
 }
 
+// Opt every raster kernel into the full dynamic shared-memory range ONCE per device (not per call:
+// the call may be inside a CUDA-graph capture).  F = 65535 needs 8 KB + 32 KB + 128 KB.
+static int ensure_smem_attrs() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64 || done[dev]) return 0;
+    const int cap = 200 * 1024;
+#define UMR_SET(K)                                                                        \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);         \
+    if (e != cudaSuccess) return (int)e;
+    UMR_SET(k_raster_fwd<0>) UMR_SET(k_raster_fwd<1>)
+    UMR_SET((k_raster_bwd<0, false>)) UMR_SET((k_raster_bwd<0, true>))
+    UMR_SET((k_raster_bwd<1, false>)) UMR_SET((k_raster_bwd<1, true>))
+#undef UMR_SET
+    done[dev] = true;
+    return 0;
+}
+
 static size_t raster_dyn_smem(int F) { return smem_list_off(F) + (((size_t)F * 2 + 15) & ~(size_t)15); }
 
 extern "C" int umr_raster_forward(const float* face_vertices, const float* textures, float* images,
@@ -849,6 +869,8 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     if (!face_vertices || !textures || !images || !aggrs_info || !workspace) return UMR_ERR_BAD_ARG;
     if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
+    rc = ensure_smem_attrs();
+    if (rc) return rc;
     const int B = p->batch_size, F = p->num_faces;
     const Consts K = make_consts(p);
     if (!K.aa && soft_colors == nullptr) soft_colors = images;
@@ -877,15 +899,11 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();
     if (softmax) {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(k_raster_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_raster_fwd<1><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
                                                      want_p2f ? p2f_acc : nullptr, ubox, K, p->eps,
                                                      p->background_color[0], p->background_color[1],
                                                      p->background_color[2]);
     } else {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(k_raster_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_raster_fwd<0><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
                                                      nullptr, ubox, K, p->eps, p->background_color[0],
                                                      p->background_color[1], p->background_color[2]);
@@ -914,6 +932,8 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         return UMR_ERR_BAD_ARG;
     if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
+    rc = ensure_smem_attrs();
+    if (rc) return rc;
     const int B = p->batch_size, F = p->num_faces;
     const Consts K = make_consts(p);
     const WorkspaceLayout L = ws_layout(B, F);
@@ -939,9 +959,6 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
 #define UMR_LAUNCH_BWD(RGBM, TG)                                                                        \
     do {                                                                                                \
-        if (smem > 48 * 1024)                                                                           \
-            cudaFuncSetAttribute(k_raster_bwd<RGBM, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 (int)smem);                                                            \
         k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                             grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)

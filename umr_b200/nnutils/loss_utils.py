@@ -49,7 +49,11 @@ def texture_loss(img_pred, img_gt, mask_gt):
 
 
 def texture_loss_masks(img_pred, img_gt, mask_gt, mask_pred, avg=True):
-    """loss_utils.py:103-116."""
+    """loss_utils.py:103-116.  CUDA tensors: one fused reduction kernel (+ fused backward) that reads
+    the RGB / alpha planes of the render in place; anything else: the reference's torch expression."""
+    if img_pred.is_cuda and img_pred.dim() == 4 and img_pred.size(1) in (1, 3):
+        per_image = ops.masked_l1_per_image(img_pred, img_gt, mask_gt, mask_pred)
+        return per_image.mean() if avg else per_image  # equal image sizes: mean of means == global mean
     mask_gt = mask_gt.unsqueeze(1)
     mask_pred = mask_pred.unsqueeze(1)
     if avg:

@@ -16,6 +16,15 @@ def _need_cuda(*ts):
             raise TypeError("umr_b200 ops support only cuda Tensors")
 
 
+def _batch_view(t, inner):
+    """(tensor, batch stride in elements) if `t` [B, ...] is dense within each batch item, else a copy."""
+    B = t.shape[0]
+    if t[0].is_contiguous() and t.dtype == torch.float32:
+        return t, (t.stride(0) if B > 1 else inner)
+    t = t.contiguous().float()
+    return t, inner
+
+
 # -------------------------------------------------------------------------------------------------
 # bilinear texture-flow sampler
 # -------------------------------------------------------------------------------------------------
@@ -71,14 +80,14 @@ class NegIouFunction(torch.autograd.Function):
         _need_cuda(predict, target)
         lib = _lib.load()
         B = predict.shape[0]
-        p = predict.detach().contiguous().float().view(B, -1)
         t = target.detach().contiguous().float().view(B, -1)
-        N = p.shape[1]
+        N = t.shape[1]
+        p, pbs = _batch_view(predict.detach(), N)  # e.g. the alpha plane of the RGBA render, read in place
         with torch.cuda.device(p.device):
             inter = torch.empty(B, device=p.device, dtype=torch.float32)
             uni = torch.empty_like(inter)
             loss = torch.empty_like(inter)
-            rc = lib.umr_iou_forward(_ptr(p), _ptr(t), _ptr(inter), _ptr(uni), _ptr(loss), B, N,
+            rc = lib.umr_iou_forward(_ptr(p), pbs, _ptr(t), _ptr(inter), _ptr(uni), _ptr(loss), B, N,
                                      _stream_ptr(p.device))
         _lib.check(rc, "umr_iou_forward")
         ctx.save_for_backward(t, inter, uni)
@@ -101,6 +110,54 @@ class NegIouFunction(torch.autograd.Function):
 
 def neg_iou_per_image(predict, target):
     return NegIouFunction.apply(predict, target)
+
+
+# -------------------------------------------------------------------------------------------------
+# masked L1 texture loss
+# -------------------------------------------------------------------------------------------------
+class MaskedL1Function(torch.autograd.Function):
+    """img_pred [B,C,H,W], img_gt [B,C,H,W], mask_gt [B,H,W], mask_pred [B,H,W] -> per-image
+    mean |pred*mask_pred - gt*mask_gt| [B]  (loss_utils.py:103-116, avg=False form)."""
+
+    @staticmethod
+    def forward(ctx, img_pred, img_gt, mask_gt, mask_pred):
+        _need_cuda(img_pred, img_gt, mask_gt, mask_pred)
+        lib = _lib.load()
+        B, C, H, W = img_pred.shape
+        HW = H * W
+        p, pbs = _batch_view(img_pred.detach(), C * HW)
+        mp, mbs = _batch_view(mask_pred.detach(), HW)
+        g = img_gt.detach().contiguous().float()
+        mg = mask_gt.detach().contiguous().float()
+        with torch.cuda.device(p.device):
+            loss = torch.empty(B, device=p.device, dtype=torch.float32)
+            rc = lib.umr_masked_l1_forward(_ptr(p), pbs, _ptr(mp), mbs, _ptr(g), _ptr(mg), _ptr(loss), B, C, HW,
+                                           _stream_ptr(p.device))
+        _lib.check(rc, "umr_masked_l1_forward")
+        ctx.save_for_backward(p, mp, g, mg)
+        ctx.meta = (pbs, mbs, img_pred.requires_grad, mask_pred.requires_grad, tuple(img_pred.shape),
+                    tuple(mask_pred.shape))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        p, mp, g, mg = ctx.saved_tensors
+        pbs, mbs, need_p, need_m, pshape, mshape = ctx.meta
+        B, C = pshape[0], pshape[1]
+        HW = pshape[2] * pshape[3]
+        gl = grad_loss.contiguous().float()
+        with torch.cuda.device(p.device):
+            gp = torch.empty(pshape, device=p.device, dtype=torch.float32) if need_p else None
+            gm = torch.empty(mshape, device=p.device, dtype=torch.float32) if need_m else None
+            rc = lib.umr_masked_l1_backward(_ptr(p), pbs, _ptr(mp), mbs, _ptr(g), _ptr(mg), _ptr(gl), _ptr(gp),
+                                            _ptr(gm), B, C, HW, _stream_ptr(p.device))
+        _lib.check(rc, "umr_masked_l1_backward")
+        return gp, None, None, gm
+
+
+def masked_l1_per_image(img_pred, img_gt, mask_gt, mask_pred):
+    return MaskedL1Function.apply(img_pred, img_gt, mask_gt, mask_pred)
 
 
 # -------------------------------------------------------------------------------------------------
