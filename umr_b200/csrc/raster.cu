@@ -25,6 +25,7 @@
 // decisions.  Only expf() may differ from a CPU libm by ulps.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umr_b200.h"
@@ -797,6 +798,271 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
     }
 }
 
+
+// =============================================================================================
+// backward, pair-parallel formulation
+//
+// The backward of a (pixel, face) pair depends only on per-pixel constants (incoming gradient, final
+// colour/alpha, softmax sum/max) and the face record: there is NO ordering constraint.  So instead of
+// binding a thread to a pixel and walking the face list (lanes idle whenever the face's cull box misses
+// their pixel: 46 % lane utilisation, and warps of a tile finish at very different times), the tile's
+// work is flattened to the list of candidate pairs: for every chunk face the cull box selects a
+// RECTANGLE of tile pixels (pixel-centre coordinates are monotone), the rectangle sizes are prefix-summed
+// and thread t evaluates pairs t, t+256, ...  All lanes work (until the distance cull), all warps of the
+// CTA carry the same load, and the 9 vertex gradients are combined by a segmented warp reduction (lanes
+// are sorted by face) followed by one shared atomic per (warp, face, component).
+// =============================================================================================
+template <int RGB, bool TEXGRAD>
+__device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp, float yp, const Consts& K, float g0,
+                                         float g1, float g2, float g3, float C0, float C1, float C2, float C3,
+                                         float ssum, float smax, int f, const float* __restrict__ tex_img,
+                                         float* __restrict__ gtex_img, float* gv) {
+    Frag fr;
+    if (!fragment(rc, xp, yp, K.thr, K.sigma, fr)) return false;
+    // alpha (prod): kernel.cu:577-585
+    float Cxy = (float)((double)g3 * ((double)(1 - C3) / fmax((double)(1 - fr.D), 1e-6)));
+    float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
+    clip_bary(k0, k1, k2);
+    const float zp = depth_of(rc, k0, k1, k2);
+    if (zp < K.near_ || zp > K.far_) return false;  // :592 drops the alpha gradient as well
+    const uint32_t flg = __float_as_uint(rc[R_FLG]);
+    const bool front = (flg & 8u) != 0;
+    float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
+    if (RGB == 0) {
+        if ((float)f == smax) {  // aggrs[1] = winning face id (:596)
+            if (TEXGRAD) {
+                float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                atomicAdd(gt + 0, g0);
+                atomicAdd(gt + 1, g1);
+                atomicAdd(gt + 2, g2);
+            }
+        }
+    } else if (front || K.double_side) {
+        const float zn = (K.far_ - zp) / (K.far_ - K.near_);
+        const float s = fr.D * expf((zn - smax) / K.gamma) / ssum;  // :608
+        const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+        if (TEXGRAD) {
+            atomicAdd(gtex_img + to + 0, s * g0);
+            atomicAdd(gtex_img + to + 1, s * g1);
+            atomicAdd(gtex_img + to + 2, s * g2);
+        }
+        float Crgb = 0.f;
+        Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
+        Crgb += g1 * (__ldg(tex_img + to + 1) - C1);
+        Crgb += g2 * (__ldg(tex_img + to + 2) - C2);
+        Crgb *= s;
+        Cxy += Crgb / fr.D;
+        const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
+        gz0 = Cz * k0 / rc[2] / rc[2];
+        gz1 = Cz * k1 / rc[5] / rc[5];
+        gz2 = Cz * k2 / rc[8] / rc[8];
+    }
+    Cxy *= fr.D * (1 - fr.D) / K.sigma;  // :632
+    const float q = 2 * fr.sign * Cxy;      // :640
+    gv[0] = q * (fr.t0 + fr.w0) * fr.dx;
+    gv[1] = q * (fr.t0 + fr.w0) * fr.dy;
+    gv[2] = gz0;
+    gv[3] = q * (fr.t1 + fr.w1) * fr.dx;
+    gv[4] = q * (fr.t1 + fr.w1) * fr.dy;
+    gv[5] = gz1;
+    gv[6] = q * (fr.t2 + fr.w2) * fr.dx;
+    gv[7] = q * (fr.t2 + fr.w2) * fr.dy;
+    gv[8] = gz2;
+    return true;
+}
+
+template <int RGB, bool TEXGRAD>
+__global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all,
+                                                             const float4* __restrict__ box_all,
+                                                             const float* __restrict__ textures,
+                                                             const float* __restrict__ colors_hi,
+                                                             const float* __restrict__ aggrs,
+                                                             const float* __restrict__ grad_images,
+                                                             float* __restrict__ grad_faces,
+                                                             float* __restrict__ grad_tex,
+                                                             const uint32_t* __restrict__ ubox, Consts K) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_rec = reinterpret_cast<float*>(smem_raw);
+    float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + smem_list_off(K.F));
+    __shared__ uint64_t s_bar;
+    __shared__ int s_warp_cnt[NWARP];
+    __shared__ float s_ext[4];
+    __shared__ float s_pix[10][CTA];       // g0..g3, C0..C3, ssum, smax of the tile's pixels (row-major 16x16)
+    __shared__ float s_xp[TILE], s_yp[TILE];
+    __shared__ unsigned int s_cm[CHUNK], s_rm[CHUNK];  // column / row pass masks of the chunk faces
+    __shared__ int s_off[CHUNK + 1];                  // prefix sums of the rectangle sizes
+    __shared__ uint32_t s_geo[CHUNK];                 // cx0 | w<<8 | ry0<<16 | rcp(w)<<... (see below)
+    __shared__ uint32_t s_rcpw[CHUNK];
+    __shared__ float s_g[CHUNK][9];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z;
+    const int S = K.S, F = K.F;
+    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    tile_extents(S, s_ext);
+    for (int i = tid; i < CHUNK * 9; i += CTA) (&s_g[0][0])[i] = 0.f;
+    if (tid < TILE) s_xp[tid] = pixel_coord(x0 + tid, S);
+    else if (tid < 2 * TILE) s_yp[tid - TILE] = pixel_coord(S - 1 - (y0 + tid - TILE), S);
+    __syncthreads();
+    if (tile_outside_union(ubox, b, s_ext)) return;  // uniform
+    const float4* box = box_all + (size_t)b * F;
+    const float* rec_img = rec_all + (size_t)b * F * REC_F;
+    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
+    if (n == 0) return;  // uniform
+
+    const int nchunk = (n + CHUNK - 1) / CHUNK;
+    issue_chunk(rec_img, s_list, n, 0, s_rec);
+    issue_chunk(rec_img, s_list, n, 1, s_rec);
+
+    // per-pixel inputs -> shared (thread = pixel, row-major for coalescing)
+    {
+        const int px = x0 + (tid & 15), py = y0 + (tid >> 4);
+        const size_t np = (size_t)S * S;
+        float v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+        if (px < S && py < S) {
+            const size_t p = (size_t)py * S + px;
+            if (K.aa) {  // avg_pool2d backward: g / 4
+                const size_t nq = (size_t)K.IS * K.IS;
+                const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * nq + q) * 0.25f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * np + p);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[4 + k] = __ldg(colors_hi + ((size_t)b * 4 + k) * np + p);
+            v[8] = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
+            v[9] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s_pix[k][tid] = v[k];
+    }
+    const int ncol = min(TILE, S - x0), nrow = min(TILE, S - y0);  // live extent of the tile
+    const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
+    float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * F * K.T2 * 3 : nullptr;
+
+    for (int c = 0; c < nchunk; ++c) {
+        const int st = c % NSTAGE;
+        const int cnt = min(CHUNK, n - c * CHUNK);
+        if (tid < CHUNK) { s_cm[tid] = 0u; s_rm[tid] = 0u; }
+        cp_async_wait<1>();
+        __syncthreads();  // chunk c (and s_pix on the first pass) visible; masks zeroed; s_g zero
+        const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
+        // ---- rectangles: thread (j = tid & 31, part = tid >> 5) tests 4 columns or 4 rows of face j
+        {
+            const int j = tid & 31, part = tid >> 5;
+            if (j < cnt) {
+                const float4 bb = *reinterpret_cast<const float4*>(chunk + j * REC_F + R_BOX);
+                unsigned m = 0;
+                if (part < 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int cidx = part * 4 + i;
+                        const float x = s_xp[cidx];
+                        if (cidx < ncol && !(x > bb.y || x < bb.x)) m |= 1u << cidx;
+                    }
+                    if (m) atomicOr(&s_cm[j], m);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ridx = (part - 4) * 4 + i;
+                        const float y = s_yp[ridx];
+                        if (ridx < nrow && !(y > bb.w || y < bb.z)) m |= 1u << ridx;
+                    }
+                    if (m) atomicOr(&s_rm[j], m);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {  // warp 0: rectangle sizes -> exclusive prefix sums
+            const unsigned cm = tid < cnt ? s_cm[tid] : 0u, rm = tid < cnt ? s_rm[tid] : 0u;
+            const int w = __popc(cm), h = __popc(rm);
+            const int size = w * h;
+            int incl = size;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            s_off[tid + 1] = incl;
+            if (tid == 0) s_off[0] = 0;
+            // masks are contiguous intervals (pixel-centre coordinates are monotone)
+            const int cx0 = cm ? __ffs(cm) - 1 : 0, ry0 = rm ? __ffs(rm) - 1 : 0;
+            s_geo[tid] = (uint32_t)cx0 | ((uint32_t)(w ? w : 1) << 8) | ((uint32_t)ry0 << 16);
+            s_rcpw[tid] = (65536u + (uint32_t)(w ? w : 1) - 1u) / (uint32_t)(w ? w : 1);  // exact floor(l/w) for l < 256
+        }
+        __syncthreads();
+        const int T = s_off[cnt];
+        for (int base = 0; base < T; base += CTA) {
+            const int p = base + tid;
+            const bool valid = p < T;
+            int j = 0;
+            if (valid) {
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const int t = j + sft;
+                    if (t < cnt && s_off[t] <= p) j = t;
+                }
+            }
+            float gv[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) gv[k] = 0.f;
+            bool contrib = false;
+            if (valid) {
+                const uint32_t geo = s_geo[j];
+                const int w = (geo >> 8) & 0xff;
+                const int local = p - s_off[j];
+                const int lr = (int)(((uint32_t)local * s_rcpw[j]) >> 16);
+                const int col = (int)(geo & 0xff) + (local - lr * w);
+                const int row = (int)(geo >> 16) + lr;
+                const int pix = row * TILE + col;
+                const float* rc = chunk + j * REC_F;
+                contrib = bwd_pair<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, s_pix[0][pix], s_pix[1][pix], s_pix[2][pix],
+                                                 s_pix[3][pix], s_pix[4][pix], s_pix[5][pix], s_pix[6][pix],
+                                                 s_pix[7][pix], s_pix[8][pix], s_pix[9][pix],
+                                                 (int)s_list[c * CHUNK + j], tex_img, gtex_img, gv);
+            }
+            // segmented (by face) reduction over the warp: lanes are sorted by j
+            const int key = valid ? j : -1;
+            if (__any_sync(0xffffffffu, contrib)) {
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int ok = __shfl_down_sync(0xffffffffu, key, d);
+                    const bool take = (lane + d < 32) && (ok == key);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const float o = __shfl_down_sync(0xffffffffu, gv[k], d);
+                        if (take) gv[k] += o;
+                    }
+                }
+                const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+                if (key >= 0 && (lane == 0 || prev != key)) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+                        if (gv[k] != 0.f) atomicAdd(&s_g[key][k], gv[k]);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with stage st; s_g is complete
+        for (int i = tid; i < cnt * 9; i += CTA) {  // one global atomic per (tile, face, component)
+            const float v = (&s_g[0][0])[i];
+            if (v != 0.f) {
+                const int j = i / 9, k = i - j * 9;
+                atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
+                (&s_g[0][0])[i] = 0.f;
+            }
+        }
+        issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);
+    }
+}
+
 }  // namespace umr
 
 // =============================================================================================
@@ -854,6 +1120,8 @@ static int ensure_smem_attrs() {
     UMR_SET(k_raster_fwd<0>) UMR_SET(k_raster_fwd<1>)
     UMR_SET((k_raster_bwd<0, false>)) UMR_SET((k_raster_bwd<0, true>))
     UMR_SET((k_raster_bwd<1, false>)) UMR_SET((k_raster_bwd<1, true>))
+    UMR_SET((k_raster_bwd_pairs<0, false>)) UMR_SET((k_raster_bwd_pairs<0, true>))
+    UMR_SET((k_raster_bwd_pairs<1, false>)) UMR_SET((k_raster_bwd_pairs<1, true>))
 #undef UMR_SET
     done[dev] = true;
     return 0;
@@ -957,10 +1225,19 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
     const size_t smem = raster_dyn_smem(F);
     const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
+    static const bool use_pairs = [] {  // UMR_BWD_IMPL=pixel selects the per-pixel formulation (A/B testing)
+        const char* e = getenv("UMR_BWD_IMPL");
+        return !(e && e[0] == 'p' && e[1] == 'i' && e[2] == 'x');
+    }();
 #define UMR_LAUNCH_BWD(RGBM, TG)                                                                        \
     do {                                                                                                \
-        k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
-                                                            grad_images, grad_faces, grad_textures, ubox, K); \
+        if (use_pairs)                                                                                  \
+            k_raster_bwd_pairs<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors,      \
+                                                                      aggrs_info, grad_images, grad_faces, \
+                                                                      grad_textures, ubox, K);             \
+        else                                                                                            \
+            k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+                                                                grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();
