@@ -1000,54 +1000,63 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
         }
         __syncthreads();
         const int T = s_off[cnt];
-        for (int base = 0; base < T; base += CTA) {
-            const int p = base + tid;
-            const bool valid = p < T;
-            int j = 0;
-            if (valid) {
+        // Each warp owns a contiguous run of the chunk's pairs (lanes interleaved), so a lane stays on the
+        // same face for many consecutive pairs: it accumulates the 9 vertex gradients privately and flushes
+        // them (shared atomics) only when its face changes -- no per-pair warp reduction.
+        {
+            const int warp = tid >> 5;
+            const int per_warp = ((T + NWARP * 32 - 1) / (NWARP * 32)) * 32;
+            const int wend = min(T, (warp + 1) * per_warp);
+            int cur = -1, cur_beg = 0, cur_end = 0, w = 1, cx0 = 0, ry0 = 0, f = 0;
+            uint32_t rcpw = 65536u;
+            const float* rc = chunk;
+            float acc[9];
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    const int t = j + sft;
-                    if (t < cnt && s_off[t] <= p) j = t;
-                }
-            }
-            float gv[9];
+            for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+            bool acc_any = false;
+            for (int p = warp * per_warp + lane; p < wend; p += 32) {
+                if (p >= cur_end) {  // face change (rare): flush, then locate the face owning pair p
+                    if (acc_any) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) gv[k] = 0.f;
-            bool contrib = false;
-            if (valid) {
-                const uint32_t geo = s_geo[j];
-                const int w = (geo >> 8) & 0xff;
-                const int local = p - s_off[j];
-                const int lr = (int)(((uint32_t)local * s_rcpw[j]) >> 16);
-                const int col = (int)(geo & 0xff) + (local - lr * w);
-                const int row = (int)(geo >> 16) + lr;
-                const int pix = row * TILE + col;
-                const float* rc = chunk + j * REC_F;
-                contrib = bwd_pair<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, s_pix[0][pix], s_pix[1][pix], s_pix[2][pix],
-                                                 s_pix[3][pix], s_pix[4][pix], s_pix[5][pix], s_pix[6][pix],
-                                                 s_pix[7][pix], s_pix[8][pix], s_pix[9][pix],
-                                                 (int)s_list[c * CHUNK + j], tex_img, gtex_img, gv);
-            }
-            // segmented (by face) reduction over the warp: lanes are sorted by j
-            const int key = valid ? j : -1;
-            if (__any_sync(0xffffffffu, contrib)) {
+                        for (int k = 0; k < 9; ++k)
+                            if (acc[k] != 0.f) atomicAdd(&s_g[cur][k], acc[k]);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int ok = __shfl_down_sync(0xffffffffu, key, d);
-                    const bool take = (lane + d < 32) && (ok == key);
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const float o = __shfl_down_sync(0xffffffffu, gv[k], d);
-                        if (take) gv[k] += o;
+                        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+                        acc_any = false;
                     }
-                }
-                const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-                if (key >= 0 && (lane == 0 || prev != key)) {
+                    int j = cur < 0 ? 0 : cur;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k)
-                        if (gv[k] != 0.f) atomicAdd(&s_g[key][k], gv[k]);
+                    for (int sft = 16; sft > 0; sft >>= 1) {
+                        const int t = j + sft;
+                        if (t < cnt && s_off[t] <= p) j = t;
+                    }
+                    cur = j;
+                    cur_beg = s_off[j];
+                    cur_end = s_off[j + 1];
+                    const uint32_t geo = s_geo[j];
+                    cx0 = (int)(geo & 0xff); w = (int)((geo >> 8) & 0xff); ry0 = (int)(geo >> 16);
+                    rcpw = s_rcpw[j];
+                    rc = chunk + j * REC_F;
+                    f = (int)s_list[c * CHUNK + j];
                 }
+                const int local = p - cur_beg;
+                const int lr = (int)(((uint32_t)local * rcpw) >> 16);
+                const int col = cx0 + (local - lr * w);
+                const int row = ry0 + lr;
+                const int pix = row * TILE + col;
+                float gv[9];
+                if (bwd_pair<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, s_pix[0][pix], s_pix[1][pix], s_pix[2][pix],
+                                           s_pix[3][pix], s_pix[4][pix], s_pix[5][pix], s_pix[6][pix], s_pix[7][pix],
+                                           s_pix[8][pix], s_pix[9][pix], f, tex_img, gtex_img, gv)) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acc[k] += gv[k];
+                    acc_any = true;
+                }
+            }
+            if (acc_any) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    if (acc[k] != 0.f) atomicAdd(&s_g[cur][k], acc[k]);
             }
         }
         __syncthreads();  // everyone is done with stage st; s_g is complete
