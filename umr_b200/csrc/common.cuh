@@ -59,6 +59,16 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Fire-and-forget float reductions (SASS: RED / ATOMS without return).  Written as PTX on purpose: nvcc
+// expands a plain atomicAdd(float*) whose result is unused into a warp-aggregation loop (match.any +
+// shuffles) that cost 20-40 % of the backward kernel's instructions (profiles/r01_*bwd*).
+__device__ __forceinline__ void red_add_global(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_shared(float* addr, float v) {
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(addr)), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);

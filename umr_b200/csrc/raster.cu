@@ -430,7 +430,6 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
     __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[NWARP];
     __shared__ float s_ext[4];
-    __shared__ float s_p2f[CHUNK][3];  // per-(tile, chunk face) p2f partial sums
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
@@ -445,7 +444,6 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
         fence_mbar_init();
     }
     tile_extents(S, s_ext);
-    if (RGB == 1 && tid < CHUNK * 3) (&s_p2f[0][0])[tid] = 0.f;
     __syncthreads();
 
     const float4* box = box_all + (size_t)b * F;
@@ -480,7 +478,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
         const int st = c % NSTAGE;
         const int cnt = min(CHUNK, n - c * CHUNK);
         cp_async_wait<1>();  // chunk c has landed (c+1 may still be in flight)
-        __syncthreads();     // ... for every thread; also: s_p2f is zero again
+        __syncthreads();     // ... for every thread
         const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
         // p2f partial sums of this warp: lane j owns chunk face j (registers, no shared traffic)
         float own_x = 0.f, own_y = 0.f, own_w = 0.f;
@@ -538,20 +536,13 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
             }
             bb = bbn;
         }
-        if (RGB == 1 && p2f_acc != nullptr && own_w != 0.f) {  // one shared atomic per (warp, face)
-            atomicAdd(&s_p2f[lane][0], own_x);
-            atomicAdd(&s_p2f[lane][1], own_y);
-            atomicAdd(&s_p2f[lane][2], own_w);
+        if (RGB == 1 && p2f_acc != nullptr && own_w != 0.f) {  // one global RED per (warp, face, component)
+            float* dst = p2f_acc + ((size_t)b * F + s_list[c * CHUNK + lane]) * 4;
+            red_add_global(dst + 0, own_x);
+            red_add_global(dst + 1, own_y);
+            red_add_global(dst + 2, own_w);
         }
-        __syncthreads();  // everyone is done with stage st; s_p2f is complete
-        if (RGB == 1 && p2f_acc != nullptr && tid < cnt * 3) {  // one global atomic per (tile, face)
-            const int j = tid / 3, k = tid - j * 3;
-            const float v = s_p2f[j][k];
-            if (v != 0.f) {
-                atomicAdd(p2f_acc + ((size_t)b * F + s_list[c * CHUNK + j]) * 4 + k, v);
-                s_p2f[j][k] = 0.f;
-            }
-        }
+        __syncthreads();  // everyone is done with stage st
         issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);  // commits an empty group past the end
     }
 
@@ -729,9 +720,9 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
                             if ((float)f == smax) {  // aggrs[1] = winning face id (:596)
                                 if (TEXGRAD) {
                                     float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                                    atomicAdd(gt + 0, g0);
-                                    atomicAdd(gt + 1, g1);
-                                    atomicAdd(gt + 2, g2);
+                                    red_add_global(gt + 0, g0);
+                                    red_add_global(gt + 1, g1);
+                                    red_add_global(gt + 2, g2);
                                 }
                             }
                         } else if (front || K.double_side) {
@@ -739,9 +730,9 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
                             const float s = fr.D * expf((zn - smax) / K.gamma) / ssum;  // :608
                             const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
                             if (TEXGRAD) {
-                                atomicAdd(gtex_img + to + 0, s * g0);
-                                atomicAdd(gtex_img + to + 1, s * g1);
-                                atomicAdd(gtex_img + to + 2, s * g2);
+                                red_add_global(gtex_img + to + 0, s * g0);
+                                red_add_global(gtex_img + to + 1, s * g1);
+                                red_add_global(gtex_img + to + 2, s * g2);
                             }
                             float Crgb = 0.f;
                             Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
@@ -783,14 +774,14 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
         }
         if (own_any) {  // one shared atomic per (warp, face, component)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) atomicAdd(&s_g[lane][k], own[k]);
+            for (int k = 0; k < 9; ++k) red_add_shared(&s_g[lane][k], own[k]);
         }
         __syncthreads();  // everyone is done with stage st; s_g is complete
         for (int i = tid; i < cnt * 9; i += CTA) {  // one global atomic per (tile, face, component)
             const float v = (&s_g[0][0])[i];
             if (v != 0.f) {
                 const int j = i / 9, k = i - j * 9;
-                atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
+                red_add_global(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
                 (&s_g[0][0])[i] = 0.f;
             }
         }
@@ -832,9 +823,9 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
         if ((float)f == smax) {  // aggrs[1] = winning face id (:596)
             if (TEXGRAD) {
                 float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                atomicAdd(gt + 0, g0);
-                atomicAdd(gt + 1, g1);
-                atomicAdd(gt + 2, g2);
+                red_add_global(gt + 0, g0);
+                red_add_global(gt + 1, g1);
+                red_add_global(gt + 2, g2);
             }
         }
     } else if (front || K.double_side) {
@@ -842,9 +833,9 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
         const float s = fr.D * expf((zn - smax) / K.gamma) / ssum;  // :608
         const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
         if (TEXGRAD) {
-            atomicAdd(gtex_img + to + 0, s * g0);
-            atomicAdd(gtex_img + to + 1, s * g1);
-            atomicAdd(gtex_img + to + 2, s * g2);
+            red_add_global(gtex_img + to + 0, s * g0);
+            red_add_global(gtex_img + to + 1, s * g1);
+            red_add_global(gtex_img + to + 2, s * g2);
         }
         float Crgb = 0.f;
         Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
@@ -894,7 +885,6 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     __shared__ int s_off[CHUNK + 1];                  // prefix sums of the rectangle sizes
     __shared__ uint32_t s_geo[CHUNK];                 // cx0 | w<<8 | ry0<<16 | rcp(w)<<... (see below)
     __shared__ uint32_t s_rcpw[CHUNK];
-    __shared__ float s_g[CHUNK][9];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
@@ -906,7 +896,6 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
         fence_mbar_init();
     }
     tile_extents(S, s_ext);
-    for (int i = tid; i < CHUNK * 9; i += CTA) (&s_g[0][0])[i] = 0.f;
     if (tid < TILE) s_xp[tid] = pixel_coord(x0 + tid, S);
     else if (tid < 2 * TILE) s_yp[tid - TILE] = pixel_coord(S - 1 - (y0 + tid - TILE), S);
     __syncthreads();
@@ -1000,74 +989,64 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
         }
         __syncthreads();
         const int T = s_off[cnt];
-        // Each warp owns a contiguous run of the chunk's pairs (lanes interleaved), so a lane stays on the
-        // same face for many consecutive pairs: it accumulates the 9 vertex gradients privately and flushes
-        // them (shared atomics) only when its face changes -- no per-pair warp reduction.
+        // Each warp owns a contiguous run [wbeg, wend) of the chunk's pairs and walks it face by face, so
+        // inside the inner loop all lanes work on the same face: the 9 vertex gradients are accumulated
+        // privately and combined ONCE per (warp, face) with a shuffle reduction + 9 global REDs (shared
+        // float atomics are CAS loops on this architecture and are avoided in the hot path).
         {
             const int warp = tid >> 5;
             const int per_warp = ((T + NWARP * 32 - 1) / (NWARP * 32)) * 32;
-            const int wend = min(T, (warp + 1) * per_warp);
-            int cur = -1, cur_beg = 0, cur_end = 0, w = 1, cx0 = 0, ry0 = 0, f = 0;
-            uint32_t rcpw = 65536u;
-            const float* rc = chunk;
-            float acc[9];
+            const int wbeg = min(T, warp * per_warp), wend = min(T, (warp + 1) * per_warp);
+            int j = 0;
+            if (wbeg < wend) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-            bool acc_any = false;
-            for (int p = warp * per_warp + lane; p < wend; p += 32) {
-                if (p >= cur_end) {  // face change (rare): flush, then locate the face owning pair p
-                    if (acc_any) {
-#pragma unroll
-                        for (int k = 0; k < 9; ++k)
-                            if (acc[k] != 0.f) atomicAdd(&s_g[cur][k], acc[k]);
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-                        acc_any = false;
-                    }
-                    int j = cur < 0 ? 0 : cur;
-#pragma unroll
-                    for (int sft = 16; sft > 0; sft >>= 1) {
-                        const int t = j + sft;
-                        if (t < cnt && s_off[t] <= p) j = t;
-                    }
-                    cur = j;
-                    cur_beg = s_off[j];
-                    cur_end = s_off[j + 1];
-                    const uint32_t geo = s_geo[j];
-                    cx0 = (int)(geo & 0xff); w = (int)((geo >> 8) & 0xff); ry0 = (int)(geo >> 16);
-                    rcpw = s_rcpw[j];
-                    rc = chunk + j * REC_F;
-                    f = (int)s_list[c * CHUNK + j];
-                }
-                const int local = p - cur_beg;
-                const int lr = (int)(((uint32_t)local * rcpw) >> 16);
-                const int col = cx0 + (local - lr * w);
-                const int row = ry0 + lr;
-                const int pix = row * TILE + col;
-                float gv[9];
-                if (bwd_pair<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, s_pix[0][pix], s_pix[1][pix], s_pix[2][pix],
-                                           s_pix[3][pix], s_pix[4][pix], s_pix[5][pix], s_pix[6][pix], s_pix[7][pix],
-                                           s_pix[8][pix], s_pix[9][pix], f, tex_img, gtex_img, gv)) {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) acc[k] += gv[k];
-                    acc_any = true;
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const int t = j + sft;
+                    if (t < cnt && s_off[t] <= wbeg) j = t;
                 }
             }
-            if (acc_any) {
+            for (; j < cnt && s_off[j] < wend; ++j) {
+                const int fbeg = s_off[j], fend = s_off[j + 1];
+                const int lo = max(wbeg, fbeg), hi = min(wend, fend);
+                if (lo >= hi) continue;  // empty rectangle
+                const uint32_t geo = s_geo[j];
+                const int cx0 = (int)(geo & 0xff), w = (int)((geo >> 8) & 0xff), ry0 = (int)(geo >> 16);
+                const uint32_t rcpw = s_rcpw[j];
+                const float* rc = chunk + j * REC_F;
+                const int f = (int)s_list[c * CHUNK + j];
+                float acc[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k)
-                    if (acc[k] != 0.f) atomicAdd(&s_g[cur][k], acc[k]);
+                for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+                bool acc_any = false;
+                for (int p = lo + lane; p < hi; p += 32) {
+                    const int local = p - fbeg;
+                    const int lr = (int)(((uint32_t)local * rcpw) >> 16);
+                    const int col = cx0 + (local - lr * w);
+                    const int row = ry0 + lr;
+                    const int pix = row * TILE + col;
+                    float gv[9];
+                    if (bwd_pair<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, s_pix[0][pix], s_pix[1][pix],
+                                               s_pix[2][pix], s_pix[3][pix], s_pix[4][pix], s_pix[5][pix],
+                                               s_pix[6][pix], s_pix[7][pix], s_pix[8][pix], s_pix[9][pix], f, tex_img,
+                                               gtex_img, gv)) {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) acc[k] += gv[k];
+                        acc_any = true;
+                    }
+                }
+                if (__any_sync(0xffffffffu, acc_any)) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
+                    if (lane < 9) {
+                        float v = acc[0];
+#pragma unroll
+                        for (int k = 1; k < 9; ++k) v = (lane == k) ? acc[k] : v;
+                        if (v != 0.f) red_add_global(grad_faces + ((size_t)b * F + f) * 9 + lane, v);
+                    }
+                }
             }
         }
-        __syncthreads();  // everyone is done with stage st; s_g is complete
-        for (int i = tid; i < cnt * 9; i += CTA) {  // one global atomic per (tile, face, component)
-            const float v = (&s_g[0][0])[i];
-            if (v != 0.f) {
-                const int j = i / 9, k = i - j * 9;
-                atomicAdd(grad_faces + ((size_t)b * F + s_list[c * CHUNK + j]) * 9 + k, v);
-                (&s_g[0][0])[i] = 0.f;
-            }
-        }
+        __syncthreads();  // everyone is done with stage st
         issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);
     }
 }
