@@ -706,7 +706,13 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
                 Frag fr;
                 if (fragment(rc, xp, yp, K.thr, K.sigma, fr)) {
                     // alpha (prod): kernel.cu:577-585
-                    float Cxy = (float)((double)g3 * ((double)(1 - C3) / fmax((double)(1 - fr.D), 1e-6)));
+                    // g3 * ((1 - alpha) / max(1 - D, 1e-6)) in double (:584).  Interior pixels have alpha == 1: the quotient is
+                    // then exactly 0 and the double division would take its (very long) special-operand path, so the zero
+                    // cases are answered directly: x * 0 == 0 with the same sign rules.
+                    const float one_m_a = 1 - C3;
+                    float Cxy = (one_m_a == 0.f || g3 == 0.f)
+                                    ? g3 * one_m_a
+                                    : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
                     float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
                     clip_bary(k0, k1, k2);
                     const float zp = depth_of(rc, k0, k1, k2);
@@ -811,7 +817,13 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
     Frag fr;
     if (!fragment(rc, xp, yp, K.thr, K.sigma, fr)) return false;
     // alpha (prod): kernel.cu:577-585
-    float Cxy = (float)((double)g3 * ((double)(1 - C3) / fmax((double)(1 - fr.D), 1e-6)));
+    // g3 * ((1 - alpha) / max(1 - D, 1e-6)) in double (:584).  Interior pixels have alpha == 1: the quotient is
+    // then exactly 0 and the double division would take its (very long) special-operand path, so the zero
+    // cases are answered directly: x * 0 == 0 with the same sign rules.
+    const float one_m_a = 1 - C3;
+    float Cxy = (one_m_a == 0.f || g3 == 0.f)
+                    ? g3 * one_m_a
+                    : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
     float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
     clip_bary(k0, k1, k2);
     const float zp = depth_of(rc, k0, k1, k2);
