@@ -516,12 +516,16 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
                             const float ez = expf((zn - smax) / K.gamma);
                             ssum = ed * ssum + ez * fr.D;
                             const float a = ez * fr.D;
-                            a_x = a * gx; a_y = a * gy; a_w = a;
-                            contrib = true;
-                            const float* tx = tex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                            c0 = ed * c0 + a * __ldg(tx);
-                            c1 = ed * c1 + a * __ldg(tx + 1);
-                            c2 = ed * c2 + a * __ldg(tx + 2);
+                            // a == 0 with no max update (occluded face whose weight underflowed): the colour
+                            // update is c = 1*c + 0*texel = c and the p2f terms are 0 -- skip the texel fetch
+                            if (a != 0.f || ed != 1.f) {
+                                a_x = a * gx; a_y = a * gy; a_w = a;
+                                contrib = a != 0.f;
+                                const float* tx = tex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                                c0 = ed * c0 + a * __ldg(tx);
+                                c1 = ed * c1 + a * __ldg(tx + 1);
+                                c2 = ed * c2 + a * __ldg(tx + 2);
+                            }
                         }
                     }
                 }
@@ -840,25 +844,33 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
                 red_add_global(gt + 2, g2);
             }
         }
-    } else if (front || K.double_side) {
+    } else if ((front || K.double_side) && (g0 != 0.f || g1 != 0.f || g2 != 0.f)) {
+        // (no colour gradient at this pixel, e.g. silhouette-only losses: every term below is exactly 0)
         const float zn = (K.far_ - zp) / (K.far_ - K.near_);
         const float s = fr.D * expf((zn - smax) / K.gamma) / ssum;  // :608
-        const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-        if (TEXGRAD) {
-            red_add_global(gtex_img + to + 0, s * g0);
-            red_add_global(gtex_img + to + 1, s * g1);
-            red_add_global(gtex_img + to + 2, s * g2);
+        // s == 0 (softmax weight of an occluded face underflowed): texture gradient, C_rgb and the z
+        // gradients are all exactly 0 -- skipping them also avoids ~9 IEEE divisions with zero numerators,
+        // each of which would take the division's slow special-operand path.
+        if (s != 0.f) {
+            const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+            if (TEXGRAD) {
+                red_add_global(gtex_img + to + 0, s * g0);
+                red_add_global(gtex_img + to + 1, s * g1);
+                red_add_global(gtex_img + to + 2, s * g2);
+            }
+            float Crgb = 0.f;
+            Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
+            Crgb += g1 * (__ldg(tex_img + to + 1) - C1);
+            Crgb += g2 * (__ldg(tex_img + to + 2) - C2);
+            Crgb *= s;
+            if (Crgb != 0.f) {
+                Cxy += Crgb / fr.D;
+                const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
+                gz0 = Cz * k0 / rc[2] / rc[2];
+                gz1 = Cz * k1 / rc[5] / rc[5];
+                gz2 = Cz * k2 / rc[8] / rc[8];
+            }
         }
-        float Crgb = 0.f;
-        Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
-        Crgb += g1 * (__ldg(tex_img + to + 1) - C1);
-        Crgb += g2 * (__ldg(tex_img + to + 2) - C2);
-        Crgb *= s;
-        Cxy += Crgb / fr.D;
-        const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
-        gz0 = Cz * k0 / rc[2] / rc[2];
-        gz1 = Cz * k1 / rc[5] / rc[5];
-        gz2 = Cz * k2 / rc[8] / rc[8];
     }
     Cxy *= fr.D * (1 - fr.D) / K.sigma;  // :632
     const float q = 2 * fr.sign * Cxy;      // :640
