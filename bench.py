@@ -239,16 +239,48 @@ class Workload:
             g = GraphedStep(lambda i=i: self.step(self.dev[i], world), warmup=2 if i == 0 else 1, pool=pool)
             pool = g.pool()
             self.g_res.append(g)
-        self.g_e2e = GraphedStep(lambda: self.step(self.stage, world), warmup=1, pool=pool)
+        import torch
+        self.stage2 = [self.stage, [torch.empty_like(t) for t in self.stage]]
+        self.g_e2e2 = [GraphedStep(lambda k=k: self.step(self.stage2[k], world), warmup=1, pool=pool) for k in (0, 1)]
+        self._copy_stream = torch.cuda.Stream()
+        self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self._consumed:
+            e.record(torch.cuda.current_stream())
+        self._e2e_next = None
 
     def gstep_resident(self, i, world):
         return self.g_res[i % NUM_SETS]()
 
     def gstep_e2e(self, i, world):
+        """e2e step with the H2D copy of step i+1 overlapped with the compute of step i: two static staging
+        buffer sets (one captured graph each), a copy stream, and events in both directions.  Every step's
+        inputs still come from pinned host memory and every step's loss is still read back, all inside the
+        timed region -- this is what a prefetching data loader does."""
+        import torch
+        cur = torch.cuda.current_stream()
+        if self._e2e_next is None:                       # first step of a run: nothing prefetched yet
+            self._prefetch(i, cur)
+        k = i % 2
+        cur.wait_event(self._copied[k])                  # inputs of step i have landed in stage set k
+        loss = self.g_e2e2[k]()
+        self._consumed[k].record(cur)                    # stage set k may be overwritten after this point
+        self._prefetch(i + 1, cur)                       # H2D of step i+1 runs under the compute of step i
+        return float(loss.item())                        # D2H read of the step's result (syncs this stream)
+
+    def _prefetch(self, i, cur):
+        import torch
+        k = i % 2
         h = self.host[i % NUM_SETS]
-        for s, t in zip(self.stage, h):
-            s.copy_(t, non_blocking=True)
-        return float(self.g_e2e().item())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed[k])
+            for s, t in zip(self.stage2[k], h):
+                s.copy_(t, non_blocking=True)
+            self._copied[k].record(self._copy_stream)
+        self._e2e_next = i
+
+    def reset_e2e(self):
+        self._e2e_next = None
 
 
 def run_gpu(args, cfg):
@@ -309,6 +341,7 @@ def run_gpu(args, cfg):
     if use_graph:
         wl.capture(world)
         ms_res, _, clocks, _ = timed(wl.gstep_resident)
+        wl.reset_e2e()
         ms_e2e, _, clocks_e2e, _ = timed(wl.gstep_e2e)
     else:
         ms_res, clocks = ms_eager, clocks_eager
@@ -338,7 +371,9 @@ def run_gpu(args, cfg):
                          "buffers)" % NUM_SETS,
                    "cuda_graph": use_graph, "eager_ms_per_step": ms_eager / K},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / K},
+                "ms_per_step": ms_e2e / K,
+                "pipeline": "H2D of step i+1 (copy stream, pinned memory) overlaps the graph replay of step i; "
+                            "loss.item() every step" if use_graph else "H2D, eager step, loss.item() in sequence"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_raster_bwd<softmax,texgrad>", "achieved": achieved, "peak": peak,

@@ -377,6 +377,7 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ rec_img, c
 struct Consts {
     float thr, sigma, gamma, near_, far_, inv_unused;
     int F, T2, R, S, IS, aa, double_side;
+    int debug;  // UMR_DEBUG bit mask (profiling experiments only; 0 in production)
 };
 
 // =============================================================================================
@@ -886,6 +887,73 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
     return true;
 }
 
+// Register-lean variant used by the pair-parallel kernel: the 10 per-pixel inputs stay in shared memory
+// (sp = &s_pix[0][pix], plane stride CTA) and are fetched where they are consumed, and the 9 gradients are
+// added straight into the caller's accumulators -- this keeps the kernel at <= 64 registers (4 CTAs/SM).
+template <int RGB, bool TEXGRAD>
+__device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float xp, float yp, const Consts& K,
+                                             const float* __restrict__ sp, int f, const float* __restrict__ tex_img,
+                                             float* __restrict__ gtex_img, float* acc) {
+    Frag fr;
+    if (!fragment(rc, xp, yp, K.thr, K.sigma, fr)) return false;
+    const float g3 = sp[3 * CTA];
+    const float one_m_a = 1 - sp[7 * CTA];
+    float Cxy = (one_m_a == 0.f || g3 == 0.f)
+                    ? g3 * one_m_a
+                    : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
+    float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
+    clip_bary(k0, k1, k2);
+    const float zp = depth_of(rc, k0, k1, k2);
+    if (zp < K.near_ || zp > K.far_) return false;
+    const uint32_t flg = __float_as_uint(rc[R_FLG]);
+    const bool front = (flg & 8u) != 0;
+    if (RGB == 0) {
+        if ((float)f == sp[9 * CTA]) {
+            if (TEXGRAD) {
+                float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                red_add_global(gt + 0, sp[0]);
+                red_add_global(gt + 1, sp[1 * CTA]);
+                red_add_global(gt + 2, sp[2 * CTA]);
+            }
+        }
+    } else if (front || K.double_side) {
+        const float g0 = sp[0], g1 = sp[1 * CTA], g2 = sp[2 * CTA];
+        if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
+            const float zn = (K.far_ - zp) / (K.far_ - K.near_);
+            const float s = fr.D * expf((zn - sp[9 * CTA]) / K.gamma) / sp[8 * CTA];
+            if (s != 0.f) {
+                const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                if (TEXGRAD) {
+                    red_add_global(gtex_img + to + 0, s * g0);
+                    red_add_global(gtex_img + to + 1, s * g1);
+                    red_add_global(gtex_img + to + 2, s * g2);
+                }
+                float Crgb = 0.f;
+                Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * CTA]);
+                Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * CTA]);
+                Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * CTA]);
+                Crgb *= s;
+                if (Crgb != 0.f) {
+                    Cxy += Crgb / fr.D;
+                    const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;
+                    acc[2] += Cz * k0 / rc[2] / rc[2];
+                    acc[5] += Cz * k1 / rc[5] / rc[5];
+                    acc[8] += Cz * k2 / rc[8] / rc[8];
+                }
+            }
+        }
+    }
+    Cxy *= fr.D * (1 - fr.D) / K.sigma;
+    const float q = 2 * fr.sign * Cxy;
+    acc[0] += q * (fr.t0 + fr.w0) * fr.dx;
+    acc[1] += q * (fr.t0 + fr.w0) * fr.dy;
+    acc[3] += q * (fr.t1 + fr.w1) * fr.dx;
+    acc[4] += q * (fr.t1 + fr.w1) * fr.dy;
+    acc[6] += q * (fr.t2 + fr.w2) * fr.dx;
+    acc[7] += q * (fr.t2 + fr.w2) * fr.dy;
+    return true;
+}
+
 template <int RGB, bool TEXGRAD>
 __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all,
                                                              const float4* __restrict__ box_all,
@@ -928,6 +996,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
     const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
     if (n == 0) return;  // uniform
+    if (K.debug & 2) return;
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
     issue_chunk(rec_img, s_list, n, 0, s_rec);
@@ -1029,6 +1098,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
                     if (t < cnt && s_off[t] <= wbeg) j = t;
                 }
             }
+            if (K.debug & 1) j = cnt;
             for (; j < cnt && s_off[j] < wend; ++j) {
                 const int fbeg = s_off[j], fend = s_off[j + 1];
                 const int lo = max(wbeg, fbeg), hi = min(wend, fend);
@@ -1048,15 +1118,8 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
                     const int col = cx0 + (local - lr * w);
                     const int row = ry0 + lr;
                     const int pix = row * TILE + col;
-                    float gv[9];
-                    if (bwd_pair<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, s_pix[0][pix], s_pix[1][pix],
-                                               s_pix[2][pix], s_pix[3][pix], s_pix[4][pix], s_pix[5][pix],
-                                               s_pix[6][pix], s_pix[7][pix], s_pix[8][pix], s_pix[9][pix], f, tex_img,
-                                               gtex_img, gv)) {
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) acc[k] += gv[k];
+                    if (bwd_pair_acc<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, &s_pix[0][pix], f, tex_img, gtex_img, acc))
                         acc_any = true;
-                    }
                 }
                 if (__any_sync(0xffffffffu, acc_any)) {
 #pragma unroll
@@ -1114,6 +1177,10 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.aa = p->anti_aliasing ? 1 : 0;
     K.S = p->image_size * (K.aa ? 2 : 1);
     K.double_side = p->double_side ? 1 : 0;
+    {
+        static const int dbg = [] { const char* e = getenv("UMR_DEBUG"); return e ? atoi(e) : 0; }();
+        K.debug = dbg;
+    }
     return K;
 }
 
