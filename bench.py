@@ -358,6 +358,14 @@ def run_gpu(args, cfg):
     achieved = (bwd_b * B) / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     fwd_achieved = (fwd_b * B) / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
 
+    traffic = None
+    try:  # dram bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if cfg["name"] == "C2":
+            traffic = tj["k_raster_bwd"]["bytes"]
+    except Exception:
+        traffic = None
     out = {
         "metric": "render fwd+bwd images/sec @256x256 1280-face mesh" if cfg["name"] == "C2"
         else "render fwd+bwd images/sec (%s)" % cfg["name"],
@@ -376,8 +384,8 @@ def run_gpu(args, cfg):
                             "loss.item() every step" if use_graph else "H2D, eager step, loss.item() in sequence"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_raster_bwd<softmax,texgrad>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_raster_bwd_pairs<softmax,texgrad>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "kernel_ms": bwd_ms,
                      "timing": "CUDA events recorded by the C ABI around the kernel launch, %d eager steps of the same "
                                "workload inside this run" % K,
