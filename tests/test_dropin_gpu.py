@@ -150,3 +150,32 @@ def test_fused_vertex_pipeline_matches_torch_glue(ambient_only, with_tex):
         ok, msg = rel_report(k, a[k], b[k], 2e-4, at * scale)
         print(msg)
         assert ok, msg
+
+
+def test_part_matching_loss_packed_renders_match_reference_pattern():
+    """part_matching_loss (loss_utils.py:333-440): the 2 packed renders give the same projections as the
+    reference's 4 separate one-hot renders; loss and gradients agree."""
+    B, IS, T = 2, 32, 2
+    rng = np.random.default_rng(11)
+    v, f = synth.icosphere(2)
+    F_ = f.shape[0]
+    part = rng.integers(0, 5, size=(F_, T * T))
+    one_hot = torch.zeros(1, F_, T * T, 5)
+    one_hot.scatter_(3, torch.from_numpy(part)[None, :, :, None], 1.0)
+    verts0 = torch.from_numpy(synth.bird_like(v, rng, B))
+    faces = torch.from_numpy(f.astype(np.int64))[None].repeat(B, 1, 1).to(DEV)
+    cams = torch.from_numpy(synth.cameras(rng, B)).to(DEV)
+    part_segs = torch.rand(B, 5, IS, IS, generator=torch.Generator().manual_seed(1)).to(DEV)
+    outs = []
+    for pack in (True, False):
+        m = loss_utils.part_matching_loss(None, None, 0, im_size=IS, batch_size=B, tex_size=T, stex_one_hot=one_hot).to(DEV)
+        m.pack_parts = pack
+        vv = verts0.clone().to(DEV).requires_grad_(True)
+        loss, projs = m(vv, faces, cams, part_segs)
+        loss.backward()
+        outs.append((loss.item(), [p.detach().cpu() for p in projs], vv.grad.cpu()))
+    for pa, pb in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(pa, pb)
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * max(1.0, abs(outs[1][0]))
+    ok, msg = rel_report("dverts", outs[0][2].numpy(), outs[1][2].numpy(), 1e-3, 1e-5 * float(outs[1][2].abs().max()))
+    assert ok, msg

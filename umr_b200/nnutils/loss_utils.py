@@ -270,13 +270,25 @@ class part_matching_loss(nn.Module):
         self.register_buffer("proj", proj)
         self.register_buffer("weights", torch.tensor([0, 5.0, 0.0, 0.0, 5.0]).view(1, 5, 1, 1))
         self.loss_type = loss_type
+        self.pack_parts = True  # 2 packed renders instead of the reference's 4 (same values)
 
     def forward(self, verts, faces, cams, part_segs, cam_probs=None, avg=True):
-        projs = []
         bs = verts.size(0)
-        for stex in (self.stex1, self.stex2, self.stex3, self.stex4):
-            p, _, _ = self.renderer(verts, faces, cams, stex[:bs])
-            projs.append(torch.mean(p[:, 0:3, :, :], dim=1).unsqueeze(1))
+        if self.pack_parts:
+            # The reference renders each one-hot part map as its own 3-identical-channel image (4 renders,
+            # loss_utils.py:385-399).  Colour channels never interact in the rasteriser, so parts 1-3 ride
+            # in the R/G/B channels of ONE render and part 4 in a second: 2 renders, identical values.  The
+            # channel-mean of the reference (mean of three equal numbers) is reproduced on a stacked copy.
+            tex123 = torch.stack((self.stex1[:bs, :, :, 0], self.stex2[:bs, :, :, 0], self.stex3[:bs, :, :, 0]), dim=-1)
+            p123, _, _ = self.renderer(verts, faces, cams, tex123)
+            p4, _, _ = self.renderer(verts, faces, cams, self.stex4[:bs])
+            projs = [torch.mean(p123[:, k:k + 1].expand(-1, 3, -1, -1), dim=1).unsqueeze(1) for k in range(3)]
+            projs.append(torch.mean(p4[:, 0:3, :, :], dim=1).unsqueeze(1))
+        else:
+            projs = []
+            for stex in (self.stex1, self.stex2, self.stex3, self.stex4):
+                p, _, _ = self.renderer(verts, faces, cams, stex[:bs])
+                projs.append(torch.mean(p[:, 0:3, :, :], dim=1).unsqueeze(1))
         proj = torch.cat([self.proj[:bs].detach()] + projs, dim=1)
         centers_proj = batch_get_centers(nn.Softmax(dim=1)(proj)[:, 1:, :, :])
         centers_parts = batch_get_centers(nn.Softmax(dim=1)(part_segs)[:, 1:, :, :])
