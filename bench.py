@@ -334,7 +334,9 @@ def run_gpu(args, cfg):
             ms = float(t.item())
         return ms, launches, clocks, sink
 
-    use_graph = not args.no_graph
+    # CUDA-graph replay only on a single GPU: capturing the NCCL all-reduce together with torch's NCCL
+    # watchdog thread is fragile (an 8-GPU capture hung in testing), so N>1 times the eager step.
+    use_graph = (not args.no_graph) and world == 1
     # eager pass: also records the raster kernels' own durations through the C-ABI event hooks
     ms_eager, launches, clocks_eager, sink = timed(wl.step_resident, profile=True)
     kern = raster.collect_profile(sink)  # {"fwd": [ms...], "bwd": [ms...]}
