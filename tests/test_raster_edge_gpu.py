@@ -121,7 +121,23 @@ def test_no_grad_forward_and_texture_only_grad():
     assert ok, msg
 
 
-def test_unsupported_modes_raise():
+@pytest.mark.parametrize("dist,alpha,textype,rgb", [
+    ("barycentric", "sum", "surface", "softmax"),
+    ("hard", "hard", "surface", "hard"),
+    ("euclidean", "sum", "vertex", "softmax"),
+    ("barycentric", "prod", "vertex", "hard"),
+    ("hard", "prod", "surface", "softmax"),
+])
+def test_modes_umr_does_not_use(dist, alpha, textype, rgb):
+    """the remaining soft_rasterize modes run through the generic kernel instantiations."""
+    fv, tex = scene(2, 2, 2, seed=9)
+    if textype == "vertex":
+        tex = np.random.default_rng(10).uniform(0, 1, size=(2, fv.shape[1], 3, 3)).astype(np.float32)
+    both(fv, tex, 40, dist_func=dist, aggr_func_alpha=alpha, texture_type=textype, aggr_func_rgb=rgb,
+         sigma_val=1e-4, dist_eps=1e-4, gamma_val=1e-3)
+
+
+def test_bad_mode_arguments_raise():
     fv, tex = scene(1, 1, 1)
-    with pytest.raises(RuntimeError):
-        raster.soft_rasterize(torch.from_numpy(fv).to(DEV), torch.from_numpy(tex).to(DEV), 16, dist_func="barycentric")
+    with pytest.raises(RuntimeError):   # vertex textures must be [B,F,3,3]
+        raster.soft_rasterize(torch.from_numpy(fv).to(DEV), torch.from_numpy(tex).to(DEV), 16, texture_type="vertex")

@@ -295,6 +295,77 @@ __device__ __forceinline__ int texel_index(float c0, float c1, int R) {  // kern
     return (R - 1 - wy) * R + (R - 1 - wx);
 }
 
+struct Consts {
+    float thr, sigma, gamma, near_, far_, inv_unused;
+    int F, T2, R, S, IS, aa, double_side;
+    int debug;  // UMR_DEBUG bit mask (profiling experiments only; 0 in production)
+    int dist, alpha, tex;  // mode ids (read only by the GEN=true instantiations)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Modes UMR does not exercise: hard / barycentric distance, hard / sum alpha, per-vertex
+// textures.  They run through the GEN=true instantiations of the per-pixel kernels, which read the mode
+// ids from Consts at run time; the UMR configuration (euclidean, prod, surface) keeps its own
+// specialised instantiations.
+// ---------------------------------------------------------------------------------------------
+template <bool GEN>
+__device__ __forceinline__ bool fragment_any(const float* __restrict__ rc, float xp, float yp, const Consts& K, Frag& fr) {
+    if (!GEN || K.dist == UMR_DIST_EUCLIDEAN) return fragment(rc, xp, yp, K.thr, K.sigma, fr);
+    const float w0 = rc[R_INV + 0] * xp + rc[R_INV + 1] * yp + rc[R_INV + 2];
+    const float w1 = rc[R_INV + 3] * xp + rc[R_INV + 4] * yp + rc[R_INV + 5];
+    const float w2 = rc[R_INV + 6] * xp + rc[R_INV + 7] * yp + rc[R_INV + 8];
+    fr.w0 = w0; fr.w1 = w1; fr.w2 = w2;
+    fr.t0 = w0; fr.t1 = w1; fr.t2 = w2;  // kernel.cu:551 (barycentric backward uses the unclipped w)
+    fr.sign = 0.f; fr.dx = 0.f; fr.dy = 0.f; fr.dis = 0.f;
+    if (K.dist == UMR_DIST_HARD) {  // kernel.cu:370-372
+        const bool inside = w0 <= 1 && w0 >= 0 && w1 <= 1 && w1 >= 0 && w2 <= 1 && w2 >= 0;
+        fr.D = inside ? 1.f : 0.f;
+        return inside;
+    }
+    // barycentric distance, kernel.cu:156-159, 374-377
+    float m = w0 > w1 ? (w1 > w2 ? w2 : w1) : (w0 > w2 ? w2 : w0);
+    const float dis = m > 0 ? m * m : -(m * m);
+    if (-dis >= K.thr) return false;
+    fr.dis = dis;
+    fr.D = (float)(1. / (1. + (double)expf(-dis / K.sigma)));
+    return true;
+}
+
+// colour channel k of face texture `tx` (surface: [T2,3] texels; vertex: [3,3] corner colours), kernel.cu:179-195
+template <bool GEN>
+__device__ __forceinline__ void sample_texture(const float* __restrict__ tx, float c0, float c1, float c2, const Consts& K,
+                                               float& r, float& g, float& b) {
+    if (!GEN || K.tex == UMR_TEX_SURFACE) {
+        const float* t = tx + (size_t)texel_index(c0, c1, K.R) * 3;
+        r = __ldg(t); g = __ldg(t + 1); b = __ldg(t + 2);
+    } else {
+        r = c0 * __ldg(tx + 0) + c1 * __ldg(tx + 3) + c2 * __ldg(tx + 6);
+        g = c0 * __ldg(tx + 1) + c1 * __ldg(tx + 4) + c2 * __ldg(tx + 7);
+        b = c0 * __ldg(tx + 2) + c1 * __ldg(tx + 5) + c2 * __ldg(tx + 8);
+    }
+}
+
+// texture gradient of one pair: adds wgt * (g0,g1,g2) to the sampled texel (surface) or w_j * wgt * g to the
+// three corner colours (vertex), kernel.cu:597-601 / 610-616 with the intended texel semantics (App. B-1)
+template <bool GEN>
+__device__ __forceinline__ void add_texture_grad(float* __restrict__ gt, float c0, float c1, float c2, const Consts& K,
+                                                 float wgt, float g0, float g1, float g2, bool weighted) {
+    if (!GEN || K.tex == UMR_TEX_SURFACE) {
+        float* t = gt + (size_t)texel_index(c0, c1, K.R) * 3;
+        red_add_global(t + 0, weighted ? wgt * g0 : g0);
+        red_add_global(t + 1, weighted ? wgt * g1 : g1);
+        red_add_global(t + 2, weighted ? wgt * g2 : g2);
+    } else {
+        const float w[3] = {c0, c1, c2};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            red_add_global(gt + 3 * j + 0, weighted ? wgt * (w[j] * g0) : w[j] * g0);
+            red_add_global(gt + 3 * j + 1, weighted ? wgt * (w[j] * g1) : w[j] * g1);
+            red_add_global(gt + 3 * j + 2, weighted ? wgt * (w[j] * g2) : w[j] * g2);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // tile machinery shared by forward and backward
 // ---------------------------------------------------------------------------------------------
@@ -374,11 +445,6 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ rec_img, c
     cp_async_commit();
 }
 
-struct Consts {
-    float thr, sigma, gamma, near_, far_, inv_unused;
-    int F, T2, R, S, IS, aa, double_side;
-    int debug;  // UMR_DEBUG bit mask (profiling experiments only; 0 in production)
-};
 
 // =============================================================================================
 // thread <-> pixel mapping: a warp covers an 8x4 pixel block (better lane utilisation against the
@@ -416,8 +482,8 @@ __device__ __forceinline__ void tile_extents(int S, float* s_ext) {
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int RGB>  // 1 softmax, 0 hard
-__global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__ rec_all,
+template <int RGB, bool GEN>  // RGB: 1 softmax, 0 hard; GEN: run-time dist/alpha/texture modes
+__global__ void __launch_bounds__(CTA, GEN ? 3 : 4) k_raster_fwd(const float* __restrict__ rec_all,
                                                        const float4* __restrict__ box_all,
                                                        const float* __restrict__ textures,
                                                        float* __restrict__ images, float* __restrict__ colors_hi,
@@ -455,7 +521,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
     // (build_tile_list ends with __syncthreads: the list is visible)
 
     // pixel state (kernel.cu:335-348)
-    float acc_a = 1.f;  // prod alpha accumulator
+    float acc_a = (!GEN || K.alpha == UMR_ALPHA_PROD) ? 1.f : 0.f;  // alpha accumulator (kernel.cu:335-336)
     float ssum = expf(eps / K.gamma);
     float smax = eps;
     float c0, c1, c2;
@@ -492,8 +558,14 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
             bool contrib = false;
             if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
                 Frag fr;
-                if (fragment(rc, xp, yp, K.thr, K.sigma, fr)) {
-                    acc_a = (float)((double)acc_a * (1. - (double)fr.D));  // kernel.cu:396
+                if (fragment_any<GEN>(rc, xp, yp, K, fr)) {
+                    if (!GEN || K.alpha == UMR_ALPHA_PROD) {
+                        acc_a = (float)((double)acc_a * (1. - (double)fr.D));  // kernel.cu:396
+                    } else if (K.alpha == UMR_ALPHA_SUM) {
+                        acc_a += fr.D;                                         // :394
+                    } else if (fr.D > 0.5f) {
+                        acc_a = 1.f;                                           // :392 hard
+                    }
                     float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
                     clip_bary(k0, k1, k2);
                     const float zp = depth_of(rc, k0, k1, k2);
@@ -507,8 +579,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
                             if (zp < zmin && inside && (K.double_side || front)) {
                                 zmin = zp;
                                 fid = f;
-                                const float* tx = tex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                                c0 = __ldg(tx); c1 = __ldg(tx + 1); c2 = __ldg(tx + 2);
+                                sample_texture<GEN>(tex_img + (size_t)f * K.T2 * 3, k0, k1, k2, K, c0, c1, c2);
                             }
                         } else if (front || K.double_side) {
                             const float zn = (K.far_ - zp) / (K.far_ - K.near_);
@@ -522,10 +593,11 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
                             if (a != 0.f || ed != 1.f) {
                                 a_x = a * gx; a_y = a * gy; a_w = a;
                                 contrib = a != 0.f;
-                                const float* tx = tex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                                c0 = ed * c0 + a * __ldg(tx);
-                                c1 = ed * c1 + a * __ldg(tx + 1);
-                                c2 = ed * c2 + a * __ldg(tx + 2);
+                                float t0, t1, t2;
+                                sample_texture<GEN>(tex_img + (size_t)f * K.T2 * 3, k0, k1, k2, K, t0, t1, t2);
+                                c0 = ed * c0 + a * t0;
+                                c1 = ed * c1 + a * t1;
+                                c2 = ed * c2 + a * t2;
                             }
                         }
                     }
@@ -552,7 +624,10 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd(const float* __restrict__
     }
 
     // finalise (kernel.cu:443-475)
-    const float alpha = (float)(1. - (double)acc_a);
+    float alpha;
+    if (!GEN || K.alpha == UMR_ALPHA_PROD) alpha = (float)(1. - (double)acc_a);  // kernel.cu:449-451
+    else if (K.alpha == UMR_ALPHA_SUM) alpha = acc_a / K.F;                       // :447
+    else alpha = acc_a;                                                           // :445
     float o0, o1, o2, g0, g1;
     if (RGB == 0) {
         o0 = c0; o1 = c1; o2 = c2;  // background kept when no face won (c* still bg)
@@ -618,7 +693,7 @@ __global__ void k_p2f_finalize(const float* __restrict__ acc, float* __restrict_
 // =============================================================================================
 // backward
 // =============================================================================================
-template <int RGB, bool TEXGRAD>
+template <int RGB, bool TEXGRAD, bool GEN>
 __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__ rec_all,
                                                        const float4* __restrict__ box_all,
                                                        const float* __restrict__ textures,
@@ -709,15 +784,19 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
             bool contrib = false;
             if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
                 Frag fr;
-                if (fragment(rc, xp, yp, K.thr, K.sigma, fr)) {
-                    // alpha (prod): kernel.cu:577-585
-                    // g3 * ((1 - alpha) / max(1 - D, 1e-6)) in double (:584).  Interior pixels have alpha == 1: the quotient is
-                    // then exactly 0 and the double division would take its (very long) special-operand path, so the zero
-                    // cases are answered directly: x * 0 == 0 with the same sign rules.
+                if (fragment_any<GEN>(rc, xp, yp, K, fr)) {
+                    // alpha: kernel.cu:577-585 (hard alpha passes the raw gradient through, as the reference does)
                     const float one_m_a = 1 - C3;
-                    float Cxy = (one_m_a == 0.f || g3 == 0.f)
-                                    ? g3 * one_m_a
-                                    : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
+                    float Cxy;
+                    if (!GEN || K.alpha == UMR_ALPHA_PROD) {
+                        Cxy = (one_m_a == 0.f || g3 == 0.f)
+                                  ? g3 * one_m_a
+                                  : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
+                    } else if (K.alpha == UMR_ALPHA_SUM) {
+                        Cxy = g3 / K.F;
+                    } else {
+                        Cxy = g3;
+                    }
                     float k0 = fr.w0, k1 = fr.w1, k2 = fr.w2;
                     clip_bary(k0, k1, k2);
                     const float zp = depth_of(rc, k0, k1, k2);
@@ -729,44 +808,58 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
                         float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
                         if (RGB == 0) {
                             if ((float)f == smax) {  // aggrs[1] = winning face id (:596)
-                                if (TEXGRAD) {
-                                    float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                                    red_add_global(gt + 0, g0);
-                                    red_add_global(gt + 1, g1);
-                                    red_add_global(gt + 2, g2);
-                                }
+                                if (TEXGRAD)
+                                    add_texture_grad<GEN>(gtex_img + (size_t)f * K.T2 * 3, k0, k1, k2, K, 1.f, g0, g1, g2, false);
                             }
-                        } else if (front || K.double_side) {
+                        } else if ((front || K.double_side) && (g0 != 0.f || g1 != 0.f || g2 != 0.f)) {
                             const float zn = (K.far_ - zp) / (K.far_ - K.near_);
                             const float s = fr.D * expf((zn - smax) / K.gamma) / ssum;  // :608
-                            const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                            if (TEXGRAD) {
-                                red_add_global(gtex_img + to + 0, s * g0);
-                                red_add_global(gtex_img + to + 1, s * g1);
-                                red_add_global(gtex_img + to + 2, s * g2);
+                            if (s != 0.f) {
+                                if (TEXGRAD)
+                                    add_texture_grad<GEN>(gtex_img + (size_t)f * K.T2 * 3, k0, k1, k2, K, s, g0, g1, g2, true);
+                                float t0, t1, t2;
+                                sample_texture<GEN>(tex_img + (size_t)f * K.T2 * 3, k0, k1, k2, K, t0, t1, t2);
+                                float Crgb = 0.f;
+                                Crgb += g0 * (t0 - C0);
+                                Crgb += g1 * (t1 - C1);
+                                Crgb += g2 * (t2 - C2);
+                                Crgb *= s;
+                                if (Crgb != 0.f) {
+                                    Cxy += Crgb / fr.D;
+                                    const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
+                                    gz0 = Cz * k0 / rc[2] / rc[2];
+                                    gz1 = Cz * k1 / rc[5] / rc[5];
+                                    gz2 = Cz * k2 / rc[8] / rc[8];
+                                }
                             }
-                            float Crgb = 0.f;
-                            Crgb += g0 * (__ldg(tex_img + to + 0) - C0);
-                            Crgb += g1 * (__ldg(tex_img + to + 1) - C1);
-                            Crgb += g2 * (__ldg(tex_img + to + 2) - C2);
-                            Crgb *= s;
-                            Cxy += Crgb / fr.D;
-                            const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
-                            gz0 = Cz * k0 / rc[2] / rc[2];
-                            gz1 = Cz * k1 / rc[5] / rc[5];
-                            gz2 = Cz * k2 / rc[8] / rc[8];
                         }
                         Cxy *= fr.D * (1 - fr.D) / K.sigma;  // :632
-                        const float q = 2 * fr.sign * Cxy;      // :640
-                        gv[0] = q * (fr.t0 + fr.w0) * fr.dx;
-                        gv[1] = q * (fr.t0 + fr.w0) * fr.dy;
-                        gv[2] = gz0;
-                        gv[3] = q * (fr.t1 + fr.w1) * fr.dx;
-                        gv[4] = q * (fr.t1 + fr.w1) * fr.dy;
-                        gv[5] = gz1;
-                        gv[6] = q * (fr.t2 + fr.w2) * fr.dx;
-                        gv[7] = q * (fr.t2 + fr.w2) * fr.dy;
-                        gv[8] = gz2;
+                        gv[2] = gz0; gv[5] = gz1; gv[8] = gz2;
+                        if (!GEN || K.dist == UMR_DIST_EUCLIDEAN) {
+                            const float q = 2 * fr.sign * Cxy;  // :640
+                            gv[0] = q * (fr.t0 + fr.w0) * fr.dx;
+                            gv[1] = q * (fr.t0 + fr.w0) * fr.dy;
+                            gv[3] = q * (fr.t1 + fr.w1) * fr.dx;
+                            gv[4] = q * (fr.t1 + fr.w1) * fr.dy;
+                            gv[6] = q * (fr.t2 + fr.w2) * fr.dx;
+                            gv[7] = q * (fr.t2 + fr.w2) * fr.dy;
+                        } else if (K.dist == UMR_DIST_BARYCENTRIC) {  // kernel.cu:162-176
+                            const float w0 = fr.t0, w1 = fr.t1, w2 = fr.t2;  // unclipped barycentrics
+                            const int pidx = w0 > w1 ? (w1 > w2 ? 2 : 1) : (w0 > w2 ? 2 : 0);
+                            const double scale = fr.dis > 0 ? (2. * (double)sqrtf(fr.dis)) : (2. * (double)sqrtf(-fr.dis));
+#pragma unroll
+                            for (int l = 0; l < 2; ++l) {
+                                const float ip = rc[R_INV + 3 * pidx + l];
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    float gkl = 0.f;
+                                    gkl += -ip * rc[R_INV + 3 * k + 0] * xp;
+                                    gkl += -ip * rc[R_INV + 3 * k + 1] * yp;
+                                    gkl += -ip * rc[R_INV + 3 * k + 2] * 1.f;
+                                    gv[3 * k + l] = (float)((double)(gkl * Cxy) * scale);
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -1155,11 +1248,18 @@ static int check_params(const UmrRasterParams* p) {
     if (p->batch_size <= 0 || p->num_faces <= 0 || p->texture_size <= 0 || p->image_size <= 0)
         return UMR_ERR_BAD_ARG;
     if (p->num_faces > 65535 || p->batch_size > 65535) return UMR_ERR_TOO_LARGE;
-    if (p->func_id_dist != UMR_DIST_EUCLIDEAN || p->func_id_alpha != UMR_ALPHA_PROD ||
-        p->texture_sample_type != UMR_TEX_SURFACE)
+    if (p->func_id_dist < 0 || p->func_id_dist > 2 || p->func_id_alpha < 0 || p->func_id_alpha > 2 ||
+        p->texture_sample_type < 0 || p->texture_sample_type > 1)
         return UMR_ERR_UNSUPPORTED;
+    if (p->texture_sample_type == UMR_TEX_VERTEX && p->texture_size != 3) return UMR_ERR_BAD_ARG;  // [B,F,3,3]
     if (p->func_id_rgb != UMR_RGB_HARD && p->func_id_rgb != UMR_RGB_SOFTMAX) return UMR_ERR_UNSUPPORTED;
     return UMR_OK;
+}
+
+// the UMR configuration has specialised kernels; every other mode combination takes the generic ones
+static bool is_generic(const UmrRasterParams* p) {
+    return p->func_id_dist != UMR_DIST_EUCLIDEAN || p->func_id_alpha != UMR_ALPHA_PROD ||
+           p->texture_sample_type != UMR_TEX_SURFACE;
 }
 
 static Consts make_consts(const UmrRasterParams* p) {
@@ -1177,6 +1277,9 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.aa = p->anti_aliasing ? 1 : 0;
     K.S = p->image_size * (K.aa ? 2 : 1);
     K.double_side = p->double_side ? 1 : 0;
+    K.dist = p->func_id_dist;
+    K.alpha = p->func_id_alpha;
+    K.tex = p->texture_sample_type;
     {
         static const int dbg = [] { const char* e = getenv("UMR_DEBUG"); return e ? atoi(e) : 0; }();
         K.debug = dbg;
@@ -1196,9 +1299,12 @@ static int ensure_smem_attrs() {
 #define UMR_SET(K)                                                                        \
     e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);         \
     if (e != cudaSuccess) return (int)e;
-    UMR_SET(k_raster_fwd<0>) UMR_SET(k_raster_fwd<1>)
-    UMR_SET((k_raster_bwd<0, false>)) UMR_SET((k_raster_bwd<0, true>))
-    UMR_SET((k_raster_bwd<1, false>)) UMR_SET((k_raster_bwd<1, true>))
+    UMR_SET((k_raster_fwd<0, false>)) UMR_SET((k_raster_fwd<1, false>))
+    UMR_SET((k_raster_fwd<0, true>)) UMR_SET((k_raster_fwd<1, true>))
+    UMR_SET((k_raster_bwd<0, false, false>)) UMR_SET((k_raster_bwd<0, true, false>))
+    UMR_SET((k_raster_bwd<1, false, false>)) UMR_SET((k_raster_bwd<1, true, false>))
+    UMR_SET((k_raster_bwd<0, false, true>)) UMR_SET((k_raster_bwd<0, true, true>))
+    UMR_SET((k_raster_bwd<1, false, true>)) UMR_SET((k_raster_bwd<1, true, true>))
     UMR_SET((k_raster_bwd_pairs<0, false>)) UMR_SET((k_raster_bwd_pairs<0, true>))
     UMR_SET((k_raster_bwd_pairs<1, false>)) UMR_SET((k_raster_bwd_pairs<1, true>))
 #undef UMR_SET
@@ -1245,16 +1351,18 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     const size_t smem = raster_dyn_smem(F);
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();
+    const bool gen = is_generic(p);
+    float* pacc = (softmax && want_p2f) ? p2f_acc : nullptr;
+#define UMR_LAUNCH_FWD(RGBM, GENM)                                                                           \
+    k_raster_fwd<RGBM, GENM><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info, \
+                                                          pacc, ubox, K, p->eps, p->background_color[0],      \
+                                                          p->background_color[1], p->background_color[2])
     if (softmax) {
-        k_raster_fwd<1><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
-                                                     want_p2f ? p2f_acc : nullptr, ubox, K, p->eps,
-                                                     p->background_color[0], p->background_color[1],
-                                                     p->background_color[2]);
+        if (gen) UMR_LAUNCH_FWD(1, true); else UMR_LAUNCH_FWD(1, false);
     } else {
-        k_raster_fwd<0><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info,
-                                                     nullptr, ubox, K, p->eps, p->background_color[0],
-                                                     p->background_color[1], p->background_color[2]);
+        if (gen) UMR_LAUNCH_FWD(0, true); else UMR_LAUNCH_FWD(0, false);
     }
+#undef UMR_LAUNCH_FWD
     if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
     if (want_p2f) {
         if (softmax) {
@@ -1308,18 +1416,19 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         const char* e = getenv("UMR_BWD_IMPL");
         return !(e && e[0] == 'p' && e[1] == 'i' && e[2] == 'x');
     }();
-#define UMR_LAUNCH_BWD(RGBM, TG)                                                                        \
-    do {                                                                                                \
-        if (use_pairs)                                                                                  \
-            k_raster_bwd_pairs<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors,      \
-                                                                      aggrs_info, grad_images, grad_faces, \
-                                                                      grad_textures, ubox, K);             \
-        else                                                                                            \
-            k_raster_bwd<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
-                                                                grad_images, grad_faces, grad_textures, ubox, K); \
+#define UMR_LAUNCH_BWD(RGBM, TG)                                                                              \
+    do {                                                                                                      \
+        if (gen)                                                                                              \
+            k_raster_bwd<RGBM, TG, true><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+                                                                      grad_images, grad_faces, grad_textures, ubox, K); \
+        else if (use_pairs)                                                                                   \
+            k_raster_bwd_pairs<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+                                                                      grad_images, grad_faces, grad_textures, ubox, K); \
+        else                                                                                                  \
+            k_raster_bwd<RGBM, TG, false><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+                                                                       grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
-    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
-    count_launch();
+    const bool gen = is_generic(p);
     if (softmax) {
         if (grad_textures) UMR_LAUNCH_BWD(1, true); else UMR_LAUNCH_BWD(1, false);
     } else {
