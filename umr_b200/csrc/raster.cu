@@ -369,6 +369,7 @@ __device__ __forceinline__ void add_texture_grad(float* __restrict__ gt, float c
 // ---------------------------------------------------------------------------------------------
 // tile machinery shared by forward and backward
 // ---------------------------------------------------------------------------------------------
+constexpr int PT = 32;          // pixel-tile side of the pair-parallel backward kernel
 constexpr int BOX_PIECE = 2048;  // cull boxes staged per TMA bulk copy (32 KB)
 constexpr int NWARP = CTA / 32;
 
@@ -469,12 +470,12 @@ __device__ __forceinline__ PixelMap map_pixel(int S) {
 
 // tile extents in pixel-centre coordinates (monotone in the index, so the cull test is conservative);
 // four threads compute one division each and broadcast through shared memory
-__device__ __forceinline__ void tile_extents(int S, float* s_ext) {
+__device__ __forceinline__ void tile_extents(int S, float* s_ext, int tile = TILE) {
     const int t = threadIdx.x;
     if (t < 4) {
-        const int x_last_i = min(blockIdx.x * TILE + TILE - 1, S - 1);
-        const int y_last_i = min(blockIdx.y * TILE + TILE - 1, S - 1);
-        const int i = t == 0 ? blockIdx.x * TILE : t == 1 ? x_last_i : t == 2 ? S - 1 - y_last_i : S - 1 - blockIdx.y * TILE;
+        const int x_last_i = min((int)blockIdx.x * tile + tile - 1, S - 1);
+        const int y_last_i = min((int)blockIdx.y * tile + tile - 1, S - 1);
+        const int i = t == 0 ? blockIdx.x * tile : t == 1 ? x_last_i : t == 2 ? S - 1 - y_last_i : S - 1 - blockIdx.y * tile;
         s_ext[t] = pixel_coord(i, S);  // 0: x first, 1: x last, 2: y bottom, 3: y top
     }
 }
@@ -981,7 +982,7 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
 }
 
 // Register-lean variant used by the pair-parallel kernel: the 10 per-pixel inputs stay in shared memory
-// (sp = &s_pix[0][pix], plane stride CTA) and are fetched where they are consumed, and the 9 gradients are
+// (sp = &s_pix[0][pix], plane stride PT*PT) and are fetched where they are consumed, and the 9 gradients are
 // added straight into the caller's accumulators -- this keeps the kernel at <= 64 registers (4 CTAs/SM).
 template <int RGB, bool TEXGRAD>
 __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float xp, float yp, const Consts& K,
@@ -989,8 +990,8 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
                                              float* __restrict__ gtex_img, float* acc) {
     Frag fr;
     if (!fragment(rc, xp, yp, K.thr, K.sigma, fr)) return false;
-    const float g3 = sp[3 * CTA];
-    const float one_m_a = 1 - sp[7 * CTA];
+    const float g3 = sp[3 * PT * PT];
+    const float one_m_a = 1 - sp[7 * PT * PT];
     float Cxy = (one_m_a == 0.f || g3 == 0.f)
                     ? g3 * one_m_a
                     : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
@@ -1001,19 +1002,19 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
     const uint32_t flg = __float_as_uint(rc[R_FLG]);
     const bool front = (flg & 8u) != 0;
     if (RGB == 0) {
-        if ((float)f == sp[9 * CTA]) {
+        if ((float)f == sp[9 * PT * PT]) {
             if (TEXGRAD) {
                 float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
                 red_add_global(gt + 0, sp[0]);
-                red_add_global(gt + 1, sp[1 * CTA]);
-                red_add_global(gt + 2, sp[2 * CTA]);
+                red_add_global(gt + 1, sp[1 * PT * PT]);
+                red_add_global(gt + 2, sp[2 * PT * PT]);
             }
         }
     } else if (front || K.double_side) {
-        const float g0 = sp[0], g1 = sp[1 * CTA], g2 = sp[2 * CTA];
+        const float g0 = sp[0], g1 = sp[1 * PT * PT], g2 = sp[2 * PT * PT];
         if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
             const float zn = (K.far_ - zp) / (K.far_ - K.near_);
-            const float s = fr.D * expf((zn - sp[9 * CTA]) / K.gamma) / sp[8 * CTA];
+            const float s = fr.D * expf((zn - sp[9 * PT * PT]) / K.gamma) / sp[8 * PT * PT];
             if (s != 0.f) {
                 const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
                 if (TEXGRAD) {
@@ -1022,9 +1023,9 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
                     red_add_global(gtex_img + to + 2, s * g2);
                 }
                 float Crgb = 0.f;
-                Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * CTA]);
-                Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * CTA]);
-                Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * CTA]);
+                Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * PT * PT]);
+                Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * PT * PT]);
+                Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * PT * PT]);
                 Crgb *= s;
                 if (Crgb != 0.f) {
                     Cxy += Crgb / fr.D;
@@ -1048,7 +1049,7 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
 }
 
 template <int RGB, bool TEXGRAD>
-__global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all,
+__global__ void __launch_bounds__(CTA, 2) k_raster_bwd_pairs(const float* __restrict__ rec_all,
                                                              const float4* __restrict__ box_all,
                                                              const float* __restrict__ textures,
                                                              const float* __restrict__ colors_hi,
@@ -1064,8 +1065,10 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[NWARP];
     __shared__ float s_ext[4];
-    __shared__ float s_pix[10][CTA];       // g0..g3, C0..C3, ssum, smax of the tile's pixels (row-major 16x16)
-    __shared__ float s_xp[TILE], s_yp[TILE];
+    // PT x PT pixel tile (32x32: 4x the pairs per chunk of the 16x16 forward tile, so the per-tile fixed
+    // costs -- list build, rectangle set-up, barriers -- are amortised over 4x the work)
+    __shared__ float s_pix[10][PT * PT];   // g0..g3, C0..C3, ssum, smax of the tile's pixels (row-major)
+    __shared__ float s_xp[PT], s_yp[PT];
     __shared__ unsigned int s_cm[CHUNK], s_rm[CHUNK];  // column / row pass masks of the chunk faces
     __shared__ int s_off[CHUNK + 1];                  // prefix sums of the rectangle sizes
     __shared__ uint32_t s_geo[CHUNK];                 // cx0 | w<<8 | ry0<<16 | rcp(w)<<... (see below)
@@ -1074,15 +1077,15 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
     const int S = K.S, F = K.F;
-    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
+    const int x0 = blockIdx.x * PT, y0 = blockIdx.y * PT;
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    tile_extents(S, s_ext);
-    if (tid < TILE) s_xp[tid] = pixel_coord(x0 + tid, S);
-    else if (tid < 2 * TILE) s_yp[tid - TILE] = pixel_coord(S - 1 - (y0 + tid - TILE), S);
+    tile_extents(S, s_ext, PT);
+    if (tid < PT) s_xp[tid] = pixel_coord(x0 + tid, S);
+    else if (tid < 2 * PT) s_yp[tid - PT] = pixel_coord(S - 1 - (y0 + tid - PT), S);
     __syncthreads();
     if (tile_outside_union(ubox, b, s_ext)) return;  // uniform
     const float4* box = box_all + (size_t)b * F;
@@ -1095,9 +1098,9 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     issue_chunk(rec_img, s_list, n, 0, s_rec);
     issue_chunk(rec_img, s_list, n, 1, s_rec);
 
-    // per-pixel inputs -> shared (thread = pixel, row-major for coalescing)
-    {
-        const int px = x0 + (tid & 15), py = y0 + (tid >> 4);
+    // per-pixel inputs -> shared (row-major, PT*PT/CTA pixels per thread, coalesced rows)
+    for (int pi = tid; pi < PT * PT; pi += CTA) {
+        const int px = x0 + (pi % PT), py = y0 + (pi / PT);
         const size_t np = (size_t)S * S;
         float v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
         if (px < S && py < S) {
@@ -1117,9 +1120,9 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
             v[9] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
         }
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s_pix[k][tid] = v[k];
+        for (int k = 0; k < 10; ++k) s_pix[k][pi] = v[k];
     }
-    const int ncol = min(TILE, S - x0), nrow = min(TILE, S - y0);  // live extent of the tile
+    const int ncol = min(PT, S - x0), nrow = min(PT, S - y0);  // live extent of the tile
     const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
     float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * F * K.T2 * 3 : nullptr;
 
@@ -1136,18 +1139,19 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
             if (j < cnt) {
                 const float4 bb = *reinterpret_cast<const float4*>(chunk + j * REC_F + R_BOX);
                 unsigned m = 0;
+                constexpr int PER = PT / 4;  // columns (or rows) tested per thread
                 if (part < 4) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int cidx = part * 4 + i;
+                    for (int i = 0; i < PER; ++i) {
+                        const int cidx = part * PER + i;
                         const float x = s_xp[cidx];
                         if (cidx < ncol && !(x > bb.y || x < bb.x)) m |= 1u << cidx;
                     }
                     if (m) atomicOr(&s_cm[j], m);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int ridx = (part - 4) * 4 + i;
+                    for (int i = 0; i < PER; ++i) {
+                        const int ridx = (part - 4) * PER + i;
                         const float y = s_yp[ridx];
                         if (ridx < nrow && !(y > bb.w || y < bb.z)) m |= 1u << ridx;
                     }
@@ -1171,7 +1175,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
             // masks are contiguous intervals (pixel-centre coordinates are monotone)
             const int cx0 = cm ? __ffs(cm) - 1 : 0, ry0 = rm ? __ffs(rm) - 1 : 0;
             s_geo[tid] = (uint32_t)cx0 | ((uint32_t)(w ? w : 1) << 8) | ((uint32_t)ry0 << 16);
-            s_rcpw[tid] = (65536u + (uint32_t)(w ? w : 1) - 1u) / (uint32_t)(w ? w : 1);  // exact floor(l/w) for l < 256
+            s_rcpw[tid] = (65536u + (uint32_t)(w ? w : 1) - 1u) / (uint32_t)(w ? w : 1);  // exact floor(l/w), l < 1024, w <= 32
         }
         __syncthreads();
         const int T = s_off[cnt];
@@ -1210,7 +1214,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
                     const int lr = (int)(((uint32_t)local * rcpw) >> 16);
                     const int col = cx0 + (local - lr * w);
                     const int row = ry0 + lr;
-                    const int pix = row * TILE + col;
+                    const int pix = row * PT + col;
                     if (bwd_pair_acc<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, &s_pix[0][pix], f, tex_img, gtex_img, acc))
                         acc_any = true;
                 }
@@ -1312,7 +1316,11 @@ static int ensure_smem_attrs() {
     return 0;
 }
 
-static size_t raster_dyn_smem(int F) { return smem_list_off(F) + (((size_t)F * 2 + 15) & ~(size_t)15); }
+static size_t raster_dyn_smem(int F) {
+    // UMR_PAD_SMEM_KB (profiling experiments only): pad the allocation to lower the CTAs/SM limit
+    static const size_t pad = [] { const char* e = getenv("UMR_PAD_SMEM_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+    return smem_list_off(F) + (((size_t)F * 2 + 15) & ~(size_t)15) + pad;
+}
 
 extern "C" int umr_raster_forward(const float* face_vertices, const float* textures, float* images,
                                   float* soft_colors, float* aggrs_info, float* p2f_info,
@@ -1422,13 +1430,14 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
             k_raster_bwd<RGBM, TG, true><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                                       grad_images, grad_faces, grad_textures, ubox, K); \
         else if (use_pairs)                                                                                   \
-            k_raster_bwd_pairs<RGBM, TG><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+            k_raster_bwd_pairs<RGBM, TG><<<grid_pairs, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                                       grad_images, grad_faces, grad_textures, ubox, K); \
         else                                                                                                  \
             k_raster_bwd<RGBM, TG, false><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                                        grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
     const bool gen = is_generic(p);
+    const dim3 grid_pairs((K.S + PT - 1) / PT, (K.S + PT - 1) / PT, B);
     if (softmax) {
         if (grad_textures) UMR_LAUNCH_BWD(1, true); else UMR_LAUNCH_BWD(1, false);
     } else {
