@@ -1299,9 +1299,15 @@ static int ensure_smem_attrs() {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev < 0 || dev >= 64 || done[dev]) return 0;
-    const int cap = 200 * 1024;
-#define UMR_SET(K)                                                                        \
-    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);         \
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaFuncAttributes fa;
+#define UMR_SET(K)                                                                                  \
+    e = cudaFuncGetAttributes(&fa, K);                                                               \
+    if (e != cudaSuccess) return (int)e;                                                             \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
+                             optin - (int)fa.sharedSizeBytes);                                       \
     if (e != cudaSuccess) return (int)e;
     UMR_SET((k_raster_fwd<0, false>)) UMR_SET((k_raster_fwd<1, false>))
     UMR_SET((k_raster_fwd<0, true>)) UMR_SET((k_raster_fwd<1, true>))
