@@ -369,7 +369,7 @@ __device__ __forceinline__ void add_texture_grad(float* __restrict__ gt, float c
 // ---------------------------------------------------------------------------------------------
 // tile machinery shared by forward and backward
 // ---------------------------------------------------------------------------------------------
-constexpr int PT = 32;          // pixel-tile side of the pair-parallel backward kernel
+constexpr int PT = 16;          // pixel-tile side of the pair-parallel backward kernel (32 was measured slower)
 constexpr int BOX_PIECE = 2048;  // cull boxes staged per TMA bulk copy (32 KB)
 constexpr int NWARP = CTA / 32;
 
@@ -1049,7 +1049,7 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
 }
 
 template <int RGB, bool TEXGRAD>
-__global__ void __launch_bounds__(CTA, 2) k_raster_bwd_pairs(const float* __restrict__ rec_all,
+__global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all,
                                                              const float4* __restrict__ box_all,
                                                              const float* __restrict__ textures,
                                                              const float* __restrict__ colors_hi,
@@ -1065,8 +1065,7 @@ __global__ void __launch_bounds__(CTA, 2) k_raster_bwd_pairs(const float* __rest
     __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[NWARP];
     __shared__ float s_ext[4];
-    // PT x PT pixel tile (32x32: 4x the pairs per chunk of the 16x16 forward tile, so the per-tile fixed
-    // costs -- list build, rectangle set-up, barriers -- are amortised over 4x the work)
+    // PT x PT pixel tile.  PT = 32 (4x the pairs per chunk) was measured 27 % slower than 16 on C2.
     __shared__ float s_pix[10][PT * PT];   // g0..g3, C0..C3, ssum, smax of the tile's pixels (row-major)
     __shared__ float s_xp[PT], s_yp[PT];
     __shared__ unsigned int s_cm[CHUNK], s_rm[CHUNK];  // column / row pass masks of the chunk faces
