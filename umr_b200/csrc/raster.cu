@@ -3,26 +3,36 @@
 // Replaces the reference kernels external/SoftRas/soft_renderer/cuda/soft_rasterize_cuda_kernel.cu
 // :222-282 (prep), :285-476 (forward), :479-656 (backward), which run one thread per pixel over ALL
 // faces.  Design:
-//   k_prep      one thread per face -> a 128-byte face record (vertices, barycentric inverse, Gram
-//               matrix, cull box expanded by the sigmoid cut-off radius, obtuse/front flags) plus a
-//               compact float4 cull box used for binning.
-//   k_raster_*  one CTA per 16x16-pixel tile.  (1) all 256 threads scan the cull boxes of the image
-//               and ballot-compact the faces that touch the tile into an ORDER-PRESERVING index list
-//               (ascending face index is required: p2f prefix-max weights, hard z-buffer tie-break);
-//               (2) the list's 128-byte records are staged into shared memory by TMA bulk copies
-//               (cp.async.bulk + mbarrier, two stages, 32 records each) so the copy of chunk c+1
-//               overlaps the math of chunk c; (3) each thread walks the staged records for its pixel.
-//               Forward fuses the background fill, the p2f accumulation (warp-shuffle reduce -> one
-//               shared atomic per warp -> one global atomic per (tile, face)), and the 2x2 average
-//               pool (warp shuffles).  Backward fuses the pool backward and reduces the 9 per-face
-//               vertex gradients with warp shuffles + shared accumulators, flushing once per
-//               (tile, face) instead of the reference's 9 global atomics per (pixel, face).
+//   k_prep            one thread per face -> a 128-byte face record (vertices, barycentric inverse, Gram
+//                     matrix, cull box expanded by the sigmoid cut-off radius, obtuse/front flags), a
+//                     compact float4 cull box for binning, and the image's UNION cull box (tiles outside
+//                     it skip the face scan).
+//   tile list         one CTA per 16x16-pixel tile: the image's cull boxes are contiguous, so they are
+//                     staged into shared memory with ONE TMA bulk copy (cp.async.bulk + mbarrier) per
+//                     <= 2048 faces; the scan ballot-compacts the faces touching the tile into an ORDER-
+//                     PRESERVING index list (ascending face index is required: p2f prefix-max weights,
+//                     hard z-buffer tie-break).  The scattered 128-byte records of the list are gathered
+//                     with 16-byte cp.async copies, double buffered (32 records per stage).
+//   k_raster_fwd      thread = pixel (a warp = an 8x4 block): walks the staged records in face order;
+//                     fuses the background fill, the p2f accumulation (warp-shuffle reduce, totals owned
+//                     by lane j, one global RED per (warp, face)) and the 2x2 average pool (shuffles).
+//   k_raster_bwd_pairs  the backward has no ordering constraint, so the tile's work is flattened to
+//                     (pixel, face) PAIRS: each face's cull box selects a rectangle of tile pixels, the
+//                     rectangle sizes are prefix-summed and every warp owns an equal contiguous run of
+//                     pairs, walked face by face; the 9 vertex gradients are accumulated privately and
+//                     combined once per (warp, face) (shuffle reduce + 9 global REDs) instead of the
+//                     reference's 9 global atomics per (pixel, face); the pool backward is fused.
+//   k_raster_bwd      per-pixel backward (kept for the generic modes and as the A/B baseline:
+//                     UMR_BWD_IMPL=pixel).
+//   GEN=true          instantiations read the distance / alpha / texture mode ids at run time
+//                     (hard / barycentric distance, hard / sum alpha, vertex textures).
 //
 // PARITY: this translation unit is compiled with -fmad=false.  The per-(pixel, face) arithmetic is an
 // operation-for-operation twin of the reference's float instantiation (same expression order, same
 // float/double promotions -- SURVEY.md App. B-6), because the reference's output is numerically
 // chaotic on sliver faces (App. B-15) and only an identical IEEE op sequence reproduces its discrete
-// decisions.  Only expf() may differ from a CPU libm by ulps.
+// decisions.  Only expf() may differ from a CPU libm by ulps.  Shortcuts are taken only where the result
+// is provably bit-identical (double-rounding-innocuous divisions, x*0 / 0/x cases).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -298,7 +308,6 @@ __device__ __forceinline__ int texel_index(float c0, float c1, int R) {  // kern
 struct Consts {
     float thr, sigma, gamma, near_, far_, inv_unused;
     int F, T2, R, S, IS, aa, double_side;
-    int debug;  // UMR_DEBUG bit mask (profiling experiments only; 0 in production)
     int dist, alpha, tex;  // mode ids (read only by the GEN=true instantiations)
 };
 
@@ -1091,7 +1100,6 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
     const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
     if (n == 0) return;  // uniform
-    if (K.debug & 2) return;
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
     issue_chunk(rec_img, s_list, n, 0, s_rec);
@@ -1194,7 +1202,6 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
                     if (t < cnt && s_off[t] <= wbeg) j = t;
                 }
             }
-            if (K.debug & 1) j = cnt;
             for (; j < cnt && s_off[j] < wend; ++j) {
                 const int fbeg = s_off[j], fend = s_off[j + 1];
                 const int lo = max(wbeg, fbeg), hi = min(wend, fend);
@@ -1283,10 +1290,6 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.dist = p->func_id_dist;
     K.alpha = p->func_id_alpha;
     K.tex = p->texture_sample_type;
-    {
-        static const int dbg = [] { const char* e = getenv("UMR_DEBUG"); return e ? atoi(e) : 0; }();
-        K.debug = dbg;
-    }
     return K;
 }
 
@@ -1321,11 +1324,7 @@ static int ensure_smem_attrs() {
     return 0;
 }
 
-static size_t raster_dyn_smem(int F) {
-    // UMR_PAD_SMEM_KB (profiling experiments only): pad the allocation to lower the CTAs/SM limit
-    static const size_t pad = [] { const char* e = getenv("UMR_PAD_SMEM_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
-    return smem_list_off(F) + (((size_t)F * 2 + 15) & ~(size_t)15) + pad;
-}
+static size_t raster_dyn_smem(int F) { return smem_list_off(F) + (((size_t)F * 2 + 15) & ~(size_t)15); }
 
 extern "C" int umr_raster_forward(const float* face_vertices, const float* textures, float* images,
                                   float* soft_colors, float* aggrs_info, float* p2f_info,
