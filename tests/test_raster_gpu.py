@@ -88,3 +88,24 @@ def test_cpu_tensor_raises():
     fv, tex = scene(1, 2, 1)
     with pytest.raises(TypeError):
         raster.soft_rasterize(torch.from_numpy(fv), torch.from_numpy(tex), 32)
+
+
+def test_profile_event_hooks_and_launch_counter():
+    """bench.py's live kernel timing: the C ABI records an event pair around the raster kernel of every
+    forward and backward call, and counts its own launches."""
+    from umr_b200 import _lib
+    lib = _lib.load()
+    fv, tex = scene(1, 2, 1, seed=4)
+    sink = []
+    raster.set_profile_sink(sink)
+    n0 = lib.umr_launch_count()
+    try:
+        got = run_gpu(fv, tex, 32, True, "softmax", np.ones((1, 4, 32, 32), np.float32))
+    finally:
+        raster.set_profile_sink(None)
+    assert lib.umr_launch_count() - n0 == 5          # prep + raster + p2f finalize, prep + raster
+    kinds = [k for k, _, _ in sink]
+    assert kinds == ["fwd", "bwd"]
+    ms = raster.collect_profile(sink)
+    assert len(ms["fwd"]) == 1 and len(ms["bwd"]) == 1 and ms["fwd"][0] > 0 and ms["bwd"][0] > 0
+    assert got["grad_faces"] is not None

@@ -1442,6 +1442,8 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     } while (0)
     const bool gen = is_generic(p);
     const dim3 grid_pairs((K.S + PT - 1) / PT, (K.S + PT - 1) / PT, B);
+    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
+    count_launch();
     if (softmax) {
         if (grad_textures) UMR_LAUNCH_BWD(1, true); else UMR_LAUNCH_BWD(1, false);
     } else {
