@@ -309,7 +309,9 @@ def run_gpu(args, cfg):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        # a rank that dies must fail the job quickly instead of leaving the others in a collective
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     from umr_b200 import _lib, raster
     lib = _lib.load()
     torch.manual_seed(0)
@@ -449,8 +451,8 @@ def run_reference(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
