@@ -205,7 +205,7 @@ class Workload:
         self.stage = [torch.empty_like(t, device=device) for t in self.host[0]]
         self.stage2 = None
 
-    def step(self, inputs, world):
+    def step(self, inputs, world, reduce=True):
         import torch
         from umr_b200.nnutils import loss_utils
         delta, cams, imgs, masks = inputs
@@ -218,8 +218,16 @@ class Workload:
         alpha, rgb = images[:, 3], images[:, :3]
         loss = 2.5 * loss_utils.neg_iou_loss(alpha, masks) + 3.0 * loss_utils.texture_loss_masks(rgb, imgs, masks, alpha)
         loss.backward()
-        self.reducer()  # N>1: ONE NCCL all-reduce of the flat [V*3 + F*T2*3] gradient
+        if reduce:
+            self.reducer()  # N>1: ONE NCCL all-reduce of the flat [V*3 + F*T2*3] gradient
+        else:
+            self.reducer.pack()  # (graph mode: the collective itself is issued outside the captured graph)
         return loss
+
+    def finish(self):
+        """The part of a step that stays outside the CUDA graph: the NCCL all-reduce + scatter back."""
+        self.reducer.reduce()
+        self.reducer.unpack()
 
     def step_resident(self, i, world):
         return self.step(self.dev[i % NUM_SETS], world)
@@ -255,15 +263,18 @@ class Workload:
         self.g_res = []
         pool = None
         for i in range(NUM_SETS):
-            g = GraphedStep(lambda i=i: self.step(self.dev[i], world), warmup=2 if i == 0 else 1, pool=pool)
+            g = GraphedStep(lambda i=i: self.step(self.dev[i], world, reduce=False), warmup=2 if i == 0 else 1, pool=pool)
             pool = g.pool()
             self.g_res.append(g)
         if self.stage2 is None:
             self._init_e2e_pipeline()
-        self.g_e2e2 = [GraphedStep(lambda k=k: self.step(self.stage2[k], world), warmup=1, pool=pool) for k in (0, 1)]
+        self.g_e2e2 = [GraphedStep(lambda k=k: self.step(self.stage2[k], world, reduce=False), warmup=1, pool=pool)
+                       for k in (0, 1)]
 
     def gstep_resident(self, i, world):
-        return self.g_res[i % NUM_SETS]()
+        loss = self.g_res[i % NUM_SETS]()
+        self.finish()
+        return loss
 
     def gstep_e2e(self, i, world):
         """e2e step with the H2D copy of step i+1 overlapped with the compute of step i: two static staging
@@ -278,6 +289,7 @@ class Workload:
         cur.wait_event(self._copied[k])                  # inputs of step i have landed in stage set k
         loss = self.g_e2e2[k]()
         self._consumed[k].record(cur)                    # stage set k may be overwritten after this point
+        self.finish()
         self._prefetch(i + 1, cur)                       # H2D of step i+1 runs under the compute of step i
         return float(loss.item())                        # D2H read of the step's result (syncs this stream)
 
@@ -349,9 +361,9 @@ def run_gpu(args, cfg):
             ms = float(t.item())
         return ms, launches, clocks, sink
 
-    # CUDA-graph replay only on a single GPU: capturing the NCCL all-reduce together with torch's NCCL
-    # watchdog thread is fragile (an 8-GPU capture hung in testing), so N>1 times the eager step.
-    use_graph = (not args.no_graph) and world == 1
+    # The captured graph holds everything of the step EXCEPT the NCCL all-reduce (capturing the collective
+    # hung at N=8 in testing); the collective and the scatter back into .grad are issued after each replay.
+    use_graph = not args.no_graph
     # eager pass: also records the raster kernels' own durations through the C-ABI event hooks
     ms_eager, launches, clocks_eager, sink = timed(wl.step_resident, profile=True)
     kern = raster.collect_profile(sink)  # {"fwd": [ms...], "bwd": [ms...]}

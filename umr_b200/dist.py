@@ -48,11 +48,16 @@ class FlatGradAllReduce:
                 p.grad.copy_(g)
             o += n
 
-    def __call__(self):
-        self.pack()
+    def reduce(self):
+        """The one collective of the step (no-op in a single process)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat, group=self.group)  # one collective per step
+            dist.all_reduce(self.flat, group=self.group)
             if self.average:
                 self.flat.mul_(1.0 / dist.get_world_size(self.group))
+        return self.flat
+
+    def __call__(self):
+        self.pack()
+        self.reduce()
         self.unpack()
         return self.flat

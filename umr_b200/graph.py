@@ -23,7 +23,9 @@ class GraphedStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool):
+        # thread_local: CUDA calls made by other host threads (e.g. the NCCL watchdog of an initialised process
+        # group) must not invalidate this capture
+        with torch.cuda.graph(self.graph, pool=pool, capture_error_mode="thread_local"):
             self.out = fn()
 
     def pool(self):
