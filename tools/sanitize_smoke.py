@@ -1,0 +1,52 @@
+"""Tiny end-to-end exercise of every kernel, meant to be run under compute-sanitizer
+(memcheck / racecheck / initcheck) on the GPU box:
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from umr_b200 import raster, synth
+from umr_b200.nnutils import chamfer_python, geom_utils, loss_utils, smr
+
+
+def main():
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    v, f = synth.icosphere(2)
+    B, IS = 2, 24
+    verts = torch.from_numpy(synth.bird_like(v, rng, B)).to(dev).requires_grad_(True)
+    faces = torch.from_numpy(f.astype(np.int64))[None].repeat(B, 1, 1).to(dev)
+    cams = torch.from_numpy(synth.cameras(rng, B)).to(dev).requires_grad_(True)
+    imgs = torch.from_numpy(synth.smooth_images(rng, B, IS)).to(dev)
+    masks = torch.from_numpy(synth.ellipse_masks(rng, B, IS)).to(dev)
+    flow = torch.from_numpy(synth.texture_flow(rng, B, f.shape[0], 2)).to(dev).requires_grad_(True)
+    tex = geom_utils.sample_textures(flow, imgs).reshape(B, f.shape[0], 4, 3)
+    total = 0
+    for rtype in ("softmax", "hard"):
+        r = smr.SoftRenderer(IS, rtype)
+        out, p2f, aggr = r(verts, faces, cams, tex)
+        total = total + loss_utils.neg_iou_loss(out[:, 3], masks) + loss_utils.texture_loss_masks(out[:, :3], imgs, masks, out[:, 3])
+    cyc, _ = loss_utils.TexCycle()(flow, p2f.detach(), aggr[:, 1].reshape(B, -1).detach())
+    dt = torch.rand(B, 1, IS, IS, device=dev)
+    total = total + cyc + loss_utils.texture_dt_loss(flow, dt)
+    pts = torch.rand(B, 10, 2, device=dev) - 0.5
+    d1, d2, _, _ = chamfer_python.distChamfer(r.project_points(verts[:, :40], cams).contiguous(), pts)
+    total = total + d1.mean() + d2.mean()
+    # generic-mode kernels
+    fv = torch.from_numpy(synth.raster_space_faces(verts.detach().cpu().numpy(), f, cams.detach().cpu().numpy())).to(dev).requires_grad_(True)
+    vt = torch.rand(B, f.shape[0], 3, 3, device=dev, requires_grad=True)
+    o2, _, _ = raster.soft_rasterize(fv, vt, IS, dist_func="barycentric", aggr_func_alpha="sum", texture_type="vertex",
+                                     sigma_val=1e-4, dist_eps=1e-4, gamma_val=1e-3, anti_aliasing=True)
+    total = total + o2.mean()
+    total.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(verts.grad).all() and torch.isfinite(cams.grad).all() and torch.isfinite(flow.grad).all()
+    print("sanitize_smoke ok: loss %.6f" % float(total))
+
+
+if __name__ == "__main__":
+    main()
