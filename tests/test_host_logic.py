@@ -62,8 +62,8 @@ def test_mesh_lighting_transform_on_cpu():
     tr = sr.Transform("look_at", perspective=False, eye=[0, 0, -2.732])
     out = tr(sr.Mesh(verts.clone(), faces)).vertices
     assert torch.allclose(out, verts + torch.tensor([0, 0, 2.732]), atol=1e-6)
-    with pytest.raises(NotImplementedError):
-        sr.Transform("projection")
+    with pytest.raises(ValueError):
+        sr.Transform("projection")      # needs a [B,3,4] matrix, like the reference
     no_tex = sr.Mesh(verts, faces)
     assert no_tex.textures.shape == (B, f.shape[0], 1, 3) and float(no_tex.textures.min()) == 1.0
 
@@ -160,3 +160,39 @@ def test_compat_install_and_overlay(tmp_path):
         assert importlib.import_module("UMRT.nnutils.chamfer_python").distChamfer is not None
     finally:
         sys.path.remove(base)
+
+
+def test_other_camera_modes_and_vertex_normals():
+    """Generic torch path of the drop-in package for the modes UMR does not use."""
+    v, f = synth.icosphere(1)
+    verts = torch.from_numpy(v)[None].repeat(2, 1, 1)
+    faces = torch.from_numpy(f)[None].repeat(2, 1, 1)
+    # sphere: area-weighted vertex normals point radially outwards (up to the mesh's winding sign)
+    n = sr.functional.vertex_normals(verts, faces)
+    cosang = (n * verts).sum(-1)
+    assert torch.allclose(cosang.abs(), torch.ones_like(cosang), atol=1e-2) and (cosang > 0).all() or (cosang < 0).all()
+    # look == look_at when the direction points at the origin
+    eye = [0.0, 0.0, -2.5]
+    a = sr.functional.look(verts, eye, direction=[0, 0, 1], up=[0, 1, 0])
+    b = sr.functional.look_at(verts, eye)
+    assert torch.allclose(a, b, atol=1e-6)
+    # perspective: x / z / tan(angle)
+    p = sr.functional.perspective(b, angle=30.)
+    assert torch.allclose(p[..., 0], b[..., 0] / b[..., 2] / np.tan(np.pi / 6), atol=1e-6)
+    # projection with identity intrinsics and no distortion: (x/z, y/z) mapped from [0, size] to [-1, 1]
+    P = torch.eye(3, 4)[None].repeat(2, 1, 1)
+    q = sr.functional.projection(b, P, torch.zeros(2, 5), orig_size=2.0)
+    assert torch.allclose(q[..., 0], 2 * (b[..., 0] / (b[..., 2] + 1e-5) - 1.0) / 2.0, atol=1e-5)
+    t = sr.Transform("projection", P=P, orig_size=2.0)
+    assert torch.allclose(t(sr.Mesh(b.clone(), faces)).vertices, q, atol=1e-6)
+    t2 = sr.Transform("look", perspective=False, eye=eye)
+    assert torch.allclose(t2(sr.Mesh(verts.clone(), faces)).vertices[..., 2], verts[..., 2] + 2.5, atol=1e-6)
+    t2.set_eyes_from_angles(2.732, 0.0, 0.0)
+    assert np.allclose(t2.transformer._eye, (0.0, 0.0, -2.732), atol=1e-6)
+    # vertex lighting: colours scale with ambient + directional * relu(n . d)
+    tex = torch.rand(2, v.shape[0], 3)
+    mesh = sr.Mesh(verts, faces, tex.clone(), texture_type="vertex")
+    lit = sr.Lighting("vertex", 0.5, (1, 1, 1), 0.5, (1, 1, 1), (0, 1, 0))(mesh)
+    expect = tex * (0.5 + 0.5 * torch.relu(n[..., 1]))[..., None]
+    assert torch.allclose(lit.textures, expect, atol=1e-6)
+    assert mesh.face_textures.shape == (2, f.shape[0], 3, 3)

@@ -7,7 +7,8 @@ Install it under the import name the reference uses with `umr_b200.compat.instal
 from . import functional
 from .mesh import Mesh
 from .renderer import SoftRenderer
-from .transform import LookAt, Transform
+Renderer = SoftRenderer  # the reference's plain `Renderer` differs only in its rasteriser defaults
+from .transform import Look, LookAt, Projection, Transform
 from .lighting import AmbientLighting, DirectionalLighting, Lighting
 from .rasterizer import SoftRasterizer
 from .losses import LaplacianLoss, FlattenLoss

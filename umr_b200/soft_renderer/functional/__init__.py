@@ -1,4 +1,5 @@
 """Functional layer of the drop-in package (reference: SoftRas/functional/__init__.py)."""
-from .geometry import face_vertices, look_at, orthogonal, perspective
+from .geometry import (face_vertices, get_points_from_angles, look, look_at, orthogonal, perspective, projection,
+                       vertex_normals)
 from .lights import ambient_lighting, directional_lighting
 from .soft_rasterize import soft_rasterize

@@ -55,10 +55,12 @@ class Lighting(nn.Module):
             shape = (mesh.batch_size, mesh.num_vertices, 3)
         light = torch.zeros(shape, dtype=torch.float32, device=mesh.device)
         light = self.ambient(light)
-        if self.light_mode == "vertex":
-            raise NotImplementedError("vertex lighting needs vertex normals: outside the UMR hot path")
         if self._needs_normals():  # zero-intensity lights add exactly 0: skip the normal computation
+            normals = mesh.surface_normals if self.light_mode == "surface" else mesh.vertex_normals
             for directional in self.directionals:
-                light = directional(light, mesh.surface_normals)
-        mesh.textures = mesh.textures * light[:, :, None, :]
+                light = directional(light, normals)
+        if self.light_mode == "surface":
+            mesh.textures = mesh.textures * light[:, :, None, :]   # [B,F,T2,3] * [B,F,1,3]
+        else:
+            mesh.textures = mesh.textures * light                  # [B,V,3] vertex colours
         return mesh

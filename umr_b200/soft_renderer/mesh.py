@@ -96,6 +96,12 @@ class Mesh(object):
         return self._cache["sn"]
 
     @property
+    def vertex_normals(self):
+        if "vn" not in self._cache:
+            self._cache["vn"] = srf.vertex_normals(self._vertices, self._faces)
+        return self._cache["vn"]
+
+    @property
     def face_textures(self):
         if self.texture_type == "surface":
             return self._textures
