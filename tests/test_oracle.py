@@ -150,3 +150,32 @@ def test_empty_and_degenerate_inputs():
     fv_deg[0, 1, :] = np.tile(fv_deg[0, 1, 0:3], 3)
     img, _, _ = softras.render(fv_deg, tex, 16, impl="B", **UMR)
     assert np.isfinite(img).all()
+
+
+@need_a
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_configurations_match_reference_on_host(seed):
+    """Random sweep over the scalar arguments of soft_rasterize (sizes, softness, clipping planes, culling,
+    background): restatement == reference-on-host, bit for bit (single-threaded, T2 == 1 for grad_textures)."""
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 3))
+    subdiv = int(rng.integers(0, 3))
+    S = int(rng.integers(9, 70))
+    tex_res = int(rng.choice([1, 2, 3]))
+    kw = dict(sigma_val=float(10 ** rng.uniform(-5.5, -3.5)), gamma_val=float(10 ** rng.uniform(-4.5, -2)),
+              dist_eps=float(10 ** rng.uniform(-10, -3)), near=float(rng.uniform(0.5, 7.5)),
+              far=float(rng.uniform(7.8, 100)), fill_back=bool(rng.integers(0, 2)),
+              background_color=tuple(float(x) for x in rng.uniform(0, 1, 3)),
+              aggr_func_rgb=str(rng.choice(["softmax", "hard"])))
+    fv, tex = scene(B, subdiv, tex_res, seed=2000 + seed)
+    res = {}
+    for impl in "AB":
+        cfg = softras.RasterCfg(S, **kw)
+        fwd = softras.forward(fv, tex, cfg, impl=impl, nthreads=1)
+        g = np.random.default_rng(seed).normal(size=fwd["soft_colors"].shape).astype(np.float32)
+        gf, gt = softras.backward(fwd, g, cfg, impl=impl, nthreads=1)
+        res[impl] = (fwd["soft_colors"], fwd["aggrs_info"], fwd["p2f_info"], gf, gt)
+    for k, (x, y) in enumerate(zip(res["A"], res["B"])):
+        if k == 4 and tex_res != 1:
+            continue  # reference UB (App. B-1)
+        assert np.array_equal(x, y), "output %d differs for %r" % (k, kw)
