@@ -309,6 +309,7 @@ struct Consts {
     float thr, sigma, gamma, near_, far_, inv_unused;
     int F, T2, R, S, IS, aa, double_side;
     int dist, alpha, tex;  // mode ids (read only by the GEN=true instantiations)
+    int vec_store;         // 1: forward may use the shared-staged 128-bit store epilogue (alignment checked on host)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -650,20 +651,9 @@ __global__ void __launch_bounds__(CTA, GEN ? 3 : 4) k_raster_fwd(const float* __
         g0 = ssum; g1 = smax;
     }
     const size_t np = (size_t)S * S;
-    if (live) {
-        const size_t p = (size_t)py * S + px;
-        aggrs[((size_t)b * 2 + 0) * np + p] = g0;
-        aggrs[((size_t)b * 2 + 1) * np + p] = g1;
-        if (colors_hi != nullptr) {
-            colors_hi[((size_t)b * 4 + 0) * np + p] = o0;
-            colors_hi[((size_t)b * 4 + 1) * np + p] = o1;
-            colors_hi[((size_t)b * 4 + 2) * np + p] = o2;
-            colors_hi[((size_t)b * 4 + 3) * np + p] = alpha;
-        }
-    }
+    // pooled values: avg_pool2d(2,2) = ((a00 + a01) + a10) + a11, then /4 (rasterizer.py:52-53)
+    float v[4] = {o0, o1, o2, alpha};
     if (K.aa) {
-        // avg_pool2d(2,2): ((a00 + a01) + a10) + a11, then /4 (rasterizer.py:52-53)
-        float v[4] = {o0, o1, o2, alpha};
         if (n > 0) {  // uniform
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -676,6 +666,56 @@ __global__ void __launch_bounds__(CTA, GEN ? 3 : 4) k_raster_fwd(const float* __
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = (((v[k] + v[k]) + v[k]) + v[k]) * 0.25f;
         }
+    }
+    const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+    if (K.aa && K.vec_store && tx0 + TILE <= S && ty0 + TILE <= S) {  // uniform: full tile, aligned buffers
+        // Coalesced 128-bit stores: the tile's 6 raster-resolution planes (RGBA + 2 aggregation planes) and its
+        // 4 pooled planes are transposed through shared memory (the record stages are free now) so every
+        // thread issues float4 stores of 64-byte row segments instead of scattered 4-byte stores.
+        cp_async_wait<0>();
+        __syncthreads();
+        float* st = s_rec;  // 6 * 256 + 4 * 64 = 1792 floats <= NSTAGE * CHUNK * REC_F = 2048
+        const int o = (py - ty0) * TILE + (px - tx0);
+        st[0 * 256 + o] = o0; st[1 * 256 + o] = o1; st[2 * 256 + o] = o2; st[3 * 256 + o] = alpha;
+        st[4 * 256 + o] = g0; st[5 * 256 + o] = g1;
+        if ((lane & 1) == 0 && (lane & 8) == 0) {
+            const int po = ((py - ty0) >> 1) * (TILE / 2) + ((px - tx0) >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st[6 * 256 + k * 64 + po] = v[k];
+        }
+        __syncthreads();
+        for (int i = tid; i < 6 * 64; i += CTA) {
+            const int plane = i >> 6, rem = i & 63, row = rem >> 2, q = rem & 3;
+            const float4 val = *reinterpret_cast<const float4*>(st + plane * 256 + row * TILE + q * 4);
+            const size_t off = (size_t)(ty0 + row) * S + tx0 + q * 4;
+            if (plane < 4) {
+                if (colors_hi != nullptr)
+                    *reinterpret_cast<float4*>(colors_hi + ((size_t)b * 4 + plane) * np + off) = val;
+            } else {
+                *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - 4)) * np + off) = val;
+            }
+        }
+        if (tid < 64) {
+            const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
+            const float4 val = *reinterpret_cast<const float4*>(st + 6 * 256 + k * 64 + row * (TILE / 2) + q * 4);
+            const int IS = K.IS;
+            const size_t nq = (size_t)IS * IS;
+            *reinterpret_cast<float4*>(images + ((size_t)b * 4 + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) = val;
+        }
+        return;
+    }
+    if (live) {
+        const size_t p = (size_t)py * S + px;
+        aggrs[((size_t)b * 2 + 0) * np + p] = g0;
+        aggrs[((size_t)b * 2 + 1) * np + p] = g1;
+        if (colors_hi != nullptr) {
+            colors_hi[((size_t)b * 4 + 0) * np + p] = o0;
+            colors_hi[((size_t)b * 4 + 1) * np + p] = o1;
+            colors_hi[((size_t)b * 4 + 2) * np + p] = o2;
+            colors_hi[((size_t)b * 4 + 3) * np + p] = alpha;
+        }
+    }
+    if (K.aa) {
         if (live && (lane & 1) == 0 && (lane & 8) == 0) {
             const int IS = K.IS;
             const size_t q = (size_t)(py >> 1) * IS + (px >> 1);
@@ -1290,6 +1330,7 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.dist = p->func_id_dist;
     K.alpha = p->func_id_alpha;
     K.tex = p->texture_sample_type;
+    K.vec_store = 0;
     return K;
 }
 
@@ -1337,8 +1378,9 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     rc = ensure_smem_attrs();
     if (rc) return rc;
     const int B = p->batch_size, F = p->num_faces;
-    const Consts K = make_consts(p);
+    Consts K = make_consts(p);
     if (!K.aa && soft_colors == nullptr) soft_colors = images;
+    K.vec_store = (K.aa && (K.S % 8) == 0 && (((uintptr_t)images | (uintptr_t)soft_colors | (uintptr_t)aggrs_info) & 15) == 0) ? 1 : 0;
     const WorkspaceLayout L = ws_layout(B, F);
     char* ws = (char*)workspace;
     float* rec = (float*)(ws + L.rec_off);
