@@ -196,3 +196,82 @@ def test_other_camera_modes_and_vertex_normals():
     expect = tex * (0.5 + 0.5 * torch.relu(n[..., 1]))[..., None]
     assert torch.allclose(lit.textures, expect, atol=1e-6)
     assert mesh.face_textures.shape == (2, f.shape[0], 3, 3)
+
+
+def test_drop_in_constructor_tables_accept_the_reference_spellings(monkeypatch):
+    """The table-driven constructors accept the reference's positional order and keywords, expose every
+    field as an attribute, and hand the rasteriser exactly the argument tuple soft_rasterize expects."""
+    from umr_b200.soft_renderer import rasterizer as rz
+    # UMR's own construction (nnutils/smr.py:56)
+    r = sr.SoftRenderer(image_size=64, aggr_func_rgb="hard", camera_mode="look_at", sigma_val=1e-5, dist_eps=1e-10,
+                        gamma_val=1e-4, background_color=[0, 0, 0], anti_aliasing=True, perspective=False)
+    ras = r.rasterizer
+    got = {k: getattr(ras, k) for k, _ in rz.FIELDS}
+    assert got == dict(image_size=64, background_color=[0, 0, 0], near=1, far=100, anti_aliasing=True, fill_back=True,
+                       eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-10, gamma_val=1e-4,
+                       aggr_func_rgb="hard", aggr_func_alpha="prod", texture_type="surface")
+    assert r.transform.camera_mode == "look_at" and r.transform.transformer.perspective is False
+    assert r.transform.transformer.viewing_scale == 1.0 and r.transform.transformer.viewing_angle == 30
+    assert r.lighting.ambient.light_intensity == 0.5 and r.lighting.directionals[0].light_direction == (0, 1, 0)
+    # positional order of the reference: SoftRasterizer(image_size, background_color, near, far, anti_aliasing, fill_back, eps, ...)
+    p = sr.SoftRasterizer(32, (1, 1, 1), 2, 50, True, True, 1e-2)
+    assert (p.image_size, p.background_color, p.near, p.far, p.anti_aliasing, p.fill_back, p.eps) == (32, (1, 1, 1), 2, 50, True, True, 1e-2)
+    with pytest.raises(ValueError):
+        sr.SoftRasterizer(dist_func="manhattan")
+    with pytest.raises(TypeError):
+        sr.SoftRasterizer(image_sise=3)
+    with pytest.raises(TypeError):
+        sr.SoftRasterizer(32, image_size=64)
+    # the kernel call receives (fv, tex, image_size, bg, near, far, fill_back, eps, sigma, dist_func, dist_eps, gamma,
+    # aggr_rgb, aggr_alpha, texture_type, anti_aliasing) -- the signature of umr_b200.raster.soft_rasterize
+    seen = {}
+    monkeypatch.setattr(rz, "soft_rasterize", lambda *a: seen.setdefault("args", a))
+    ras.rasterize("FV", "TEX")
+    assert seen["args"] == ("FV", "TEX", 64, [0, 0, 0], 1, 100, True, 1e-3, 1e-5, "euclidean", 1e-10, 1e-4, "hard", "prod",
+                            "surface", True)
+    import inspect
+    from umr_b200 import raster
+    assert list(inspect.signature(raster.soft_rasterize).parameters)[2:] == list(rz.KERNEL_ARGS)
+    # light / camera modules positionally, like the reference's own call sites (renderer.py:62-76)
+    lt = sr.Lighting("surface", 0.8, [1, 1, 1], 0.5, [1, 1, 1], [0, 1, 0])
+    assert lt.ambient.light_intensity == 0.8 and lt.directionals[0].light_intensity == 0.5
+    tr = sr.Transform("look_at", None, None, 512, False, 30, 1.0, [0, 0, -2.732], [0, 0, 1])
+    assert tr.transformer._eye == [0, 0, -2.732] and tr.transformer.perspective is False
+    assert abs(sr.LookAt()._eye[2] + (1. / np.tan(np.radians(30)) + 1)) < 1e-12
+
+
+def test_hypothesis_tiling_and_weighting_helpers():
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 5, 2, generator=g)
+    ref = x.unsqueeze(1).repeat(1, 4, 1, 1).view(-1, 5, 2)          # loss_utils.py:260
+    assert torch.equal(loss_utils.tile_hypotheses(x, 4), ref)
+    f = torch.randint(0, 9, (3, 7, 3), generator=g)
+    assert torch.equal(loss_utils.tile_hypotheses(f, 8), f.unsqueeze(1).repeat(1, 8, 1, 1).view(-1, 7, 3))
+    per = torch.rand(12, generator=g)
+    probs = torch.softmax(torch.rand(3, 4, generator=g), 1)
+    ref = (per.view(3, -1) * probs).sum(dim=1).mean()                # loss_utils.py:271-273
+    assert torch.equal(loss_utils.expected_over_hypotheses(per, probs), ref)
+
+
+def test_corr_loss_chamfer_matches_reference_expression(monkeypatch):
+    """CorrLossChamfer.forward (loss_utils.py:223-248) on CPU, with distChamfer swapped for the torch oracle."""
+    monkeypatch.setattr(loss_utils, "distChamfer", oracle_losses.dist_chamfer)
+    g = torch.Generator().manual_seed(4)
+    B, V = 3, 60
+    parts = [torch.arange(0, 10), torch.arange(10, 30), torch.arange(30, 35), torch.arange(35, 50)]
+    m = loss_utils.CorrLossChamfer(None, 64, part_vertices=parts)
+    verts = torch.rand(B, V, 3, generator=g) - 0.5
+    cams = torch.from_numpy(synth.cameras(np.random.default_rng(0), B))
+    pts = [torch.rand(B, n, 2, generator=g) - 0.5 for n in (10, 30, 10, 30)]
+    loss, vert2d = m(pts[0], pts[1], pts[2], pts[3], verts, cams)
+    # reference expression
+    v2d = oracle_losses.orthographic_proj_withz(verts[:, torch.cat(parts)], cams)[:, :, :2]
+    nums = [10, 30, 35, 50]
+    h = oracle_losses.dist_chamfer(v2d[:, :nums[0]], pts[0])[0]
+    b = oracle_losses.dist_chamfer(v2d[:, nums[0]:nums[1]], pts[1])[0]
+    n = oracle_losses.dist_chamfer(v2d[:, nums[1]:nums[2]], pts[2])[0]
+    k = oracle_losses.dist_chamfer(v2d[:, nums[2]:nums[3]], pts[3])[0]
+    ref = torch.mean(torch.mean(torch.cat((h * 1, b * 1, n * 0, k * 0), dim=1), dim=1))
+    assert torch.allclose(vert2d, v2d, atol=1e-6) and torch.allclose(loss, ref, atol=1e-6)
+    per_sample = m(pts[0], pts[1], pts[2], pts[3], verts, cams, avg=False)
+    assert per_sample.shape == (B,)

@@ -126,19 +126,17 @@ class CorrLossChamfer(nn.Module):
         self.nums = nums
 
     def forward(self, head_points, belly_points, neck_points, back_points, verts, cams, avg=True):
-        dev = verts.device
-        idx = torch.cat((self.head_vertices, self.belly_vertices, self.neck_vertices,
-                         self.back_vertices)).to(dev)
-        vert_coords = verts[:, idx, :]
-        vert2d = self.renderer.project_points(vert_coords, cams)
-        nums = self.nums
-        head_cdist1, _, _, _ = distChamfer(vert2d[:, :nums[0], :].contiguous(), head_points)
-        belly_cdist1, _, _, _ = distChamfer(vert2d[:, nums[0]:nums[1], :].contiguous(), belly_points)
-        neck_cdist1, _, _, _ = distChamfer(vert2d[:, nums[1]:nums[2], :].contiguous(), neck_points)
-        back_cdist1, _, _, _ = distChamfer(vert2d[:, nums[2]:nums[3], :].contiguous(), back_points)
-        cdist = torch.cat((head_cdist1 * self.weights[0], belly_cdist1 * self.weights[1],
-                           neck_cdist1 * self.weights[2], back_cdist1 * self.weights[3]), dim=1)
-        loss = torch.mean(cdist, dim=1)
+        groups = (self.head_vertices, self.belly_vertices, self.neck_vertices, self.back_vertices)
+        targets = (head_points, belly_points, neck_points, back_points)
+        idx = torch.cat(groups).to(verts.device)
+        vert2d = self.renderer.project_points(verts[:, idx, :], cams)  # [B, sum(sizes), 2]
+        terms, start = [], 0
+        for group, target, weight in zip(groups, targets, self.weights):
+            stop = start + len(group)
+            d_to_target, _, _, _ = distChamfer(vert2d[:, start:stop, :].contiguous(), target)
+            terms.append(d_to_target * weight)
+            start = stop
+        loss = torch.mean(torch.cat(terms, dim=1), dim=1)
         if avg:
             return torch.mean(loss), vert2d
         return loss
@@ -147,6 +145,17 @@ class CorrLossChamfer(nn.Module):
 # ---------------------------------------------------------------------------------------------
 # multi-hypothesis render losses
 # ---------------------------------------------------------------------------------------------
+def tile_hypotheses(x, num):
+    """[B, ...] -> [B*num, ...]: every sample repeated once per camera hypothesis, hypotheses of one sample
+    adjacent (the reference's `x.unsqueeze(1).repeat(1, num, ...).view(-1, ...)`, loss_utils.py:260-261,303-305)."""
+    return x.unsqueeze(1).expand(x.size(0), num, *x.shape[1:]).reshape(x.size(0) * num, *x.shape[1:])
+
+
+def expected_over_hypotheses(per_render, cam_probs):
+    """[B*H] per-render losses -> scalar: probability-weighted sum over the H hypotheses, mean over B."""
+    return (per_render.view(cam_probs.size(0), -1) * cam_probs).sum(dim=1).mean()
+
+
 class MultiMaskLoss(nn.Module):
     """loss_utils.py:250-275: silhouette IoU over all camera hypotheses, weighted by `cam_probs`."""
 
@@ -157,18 +166,11 @@ class MultiMaskLoss(nn.Module):
         self.image_size = image_size
 
     def forward(self, vs, fs, cams_all_hypo, cam_probs, masks_gt):
-        bs = vs.size(0)
-        pred_vs = vs.unsqueeze(1).repeat(1, self.num_hypo_cams, 1, 1).view(-1, vs.size(1), 3)
-        faces = fs.unsqueeze(1).repeat(1, self.num_hypo_cams, 1, 1).view(-1, fs.size(1), 3)
-        cams_all_hypo_flat = cams_all_hypo.view(-1, 7)
-        pred, _, _ = self.renderer.forward(pred_vs, faces, cams_all_hypo_flat)
-        mask_all_hypo = pred[:, 3, :, :]
-        masks = masks_gt.unsqueeze(1).repeat(1, self.num_hypo_cams, 1, 1).view(-1, self.image_size,
-                                                                                  self.image_size)
-        loss = neg_iou_loss(mask_all_hypo, masks, avg=False)
-        loss = loss.view(bs, -1) * cam_probs
-        loss = loss.sum(dim=1)
-        return loss.mean(), mask_all_hypo
+        H = self.num_hypo_cams
+        rgba, _, _ = self.renderer.forward(tile_hypotheses(vs, H), tile_hypotheses(fs, H), cams_all_hypo.view(-1, 7))
+        mask_all_hypo = rgba[:, 3, :, :]
+        per_render = neg_iou_loss(mask_all_hypo, tile_hypotheses(masks_gt, H), avg=False)
+        return expected_over_hypotheses(per_render, cam_probs), mask_all_hypo
 
 
 class MultiTextureLoss(nn.Module):
@@ -193,25 +195,20 @@ class MultiTextureLoss(nn.Module):
 
     def forward(self, vs, fs, cams_all_hypo, cam_probs, proj_cam, rgbs, masks_gt, masks_pred, tx, tex_flow,
                 dts_barrier):
-        bs = vs.size(0)
         H = self.num_hypo_cams
-        pred_vs = vs.unsqueeze(1).repeat(1, H, 1, 1).view(-1, vs.size(1), 3)
-        faces = fs.unsqueeze(1).repeat(1, H, 1, 1).view(-1, fs.size(1), 3)
-        tex = tx.unsqueeze(1).repeat(1, H, 1, 1, 1).view(-1, tx.size(1), tx.size(2), 3)
-        cams_all_hypo_flat = cams_all_hypo.view(-1, 7)
-        texture_rgba, _, _ = self.renderer.forward(pred_vs.detach(), faces, cams_all_hypo_flat, tex)
+        # textured softmax render of every hypothesis; vertices detached: only the texture learns here (:313)
+        texture_rgba, _, _ = self.renderer.forward(tile_hypotheses(vs.detach(), H), tile_hypotheses(fs, H),
+                                                   cams_all_hypo.view(-1, 7), tile_hypotheses(tx, H))
         texture_pred = texture_rgba[:, 0:3, :, :]
-        imgs = rgbs.unsqueeze(1).repeat(1, H, 1, 1, 1).view(-1, 3, self.image_size, self.image_size)
-        masks_gt = masks_gt.unsqueeze(1).repeat(1, H, 1, 1).view(-1, self.image_size, self.image_size)
-        tex_loss = self.texture_loss(texture_pred, imgs, masks_gt, masks_pred, avg=False)
-        tex_loss = tex_loss.view(bs, -1)
-        tex_loss = (tex_loss * cam_probs).sum(dim=1).mean()
+        per_render = self.texture_loss(texture_pred, tile_hypotheses(rgbs, H), tile_hypotheses(masks_gt, H),
+                                       masks_pred, avg=False)
+        tex_loss = expected_over_hypotheses(per_render, cam_probs)
         tex_dt_loss = texture_dt_loss(tex_flow, dts_barrier)
         # visibility map from the HARD renderer; its p2f_info is identically zero (kernel.cu:417-431 is
         # softmax-only) -- reference quirk reproduced
         _, p2f_info, aggr_info = self.hard_renderer(vs.detach(), fs, proj_cam.detach())
-        aggr_info = aggr_info[:, 1, :, :].reshape(bs, -1)
-        tex_cycle_loss, avg_flow = self.texture_cycle_fn(tex_flow, p2f_info.detach(), aggr_info.detach())
+        face_ids = aggr_info[:, 1, :, :].reshape(vs.size(0), -1)
+        tex_cycle_loss, _ = self.texture_cycle_fn(tex_flow, p2f_info.detach(), face_ids.detach())
         return tex_loss, tex_dt_loss, tex_cycle_loss, texture_pred
 
 

@@ -1,16 +1,20 @@
-"""Drop-in `soft_renderer` package (the names NVlabs/UMR imports from external/SoftRas,
-`SoftRas/__init__.py:1-7`) backed by the sm_100a kernels of umr_b200.
+"""Drop-in `soft_renderer` package backed by the sm_100a kernels of umr_b200.
 
-Install it under the import name the reference uses with `umr_b200.compat.install()`:
-`import soft_renderer as sr` then resolves to this package.
+It provides the names NVlabs/UMR takes from `external/SoftRas` (SoftRas/__init__.py:1-7): the mesh container,
+the renderer and its three stages (lighting, camera transform, soft rasteriser), the two mesh regularisers
+and the `functional` layer.  `umr_b200.compat.install()` registers it under the import name `soft_renderer`.
 """
-from . import functional
-from .mesh import Mesh
-from .renderer import SoftRenderer
-Renderer = SoftRenderer  # the reference's plain `Renderer` differs only in its rasteriser defaults
-from .transform import Look, LookAt, Projection, Transform
-from .lighting import AmbientLighting, DirectionalLighting, Lighting
-from .rasterizer import SoftRasterizer
-from .losses import LaplacianLoss, FlattenLoss
-
 __version__ = "1.0.0+umr_b200"
+
+from . import functional  # noqa: E402
+from .lighting import AmbientLighting, DirectionalLighting, Lighting  # noqa: E402
+from .losses import FlattenLoss, LaplacianLoss  # noqa: E402
+from .mesh import Mesh  # noqa: E402
+from .rasterizer import SoftRasterizer  # noqa: E402
+from .renderer import SoftRenderer  # noqa: E402
+from .transform import Look, LookAt, Projection, Transform  # noqa: E402
+
+Renderer = SoftRenderer  # the reference's plain `Renderer` differs only in its rasteriser defaults
+
+__all__ = ["functional", "Mesh", "Renderer", "SoftRenderer", "Projection", "LookAt", "Look", "Transform",
+           "AmbientLighting", "DirectionalLighting", "Lighting", "SoftRasterizer", "LaplacianLoss", "FlattenLoss"]

@@ -1,66 +1,62 @@
-"""Lighting modules of the drop-in package (reference: SoftRas/lighting.py).
-
-UMR pokes `renderer.lighting.ambient.light_intensity` and
-`renderer.lighting.directionals[0].light_intensity` (nnutils/smr.py:63,70-71), so those attribute
-paths are part of the API.
-"""
+"""Lighting of the drop-in package.  Reference: SoftRas/lighting.py (module / attribute names: UMR pokes
+`renderer.lighting.ambient.light_intensity` and `renderer.lighting.directionals[0].light_intensity`,
+nnutils/smr.py:63,70-71), functional/{ambient,directional}_lighting.py (the formulas)."""
 import torch
 import torch.nn as nn
 
 from . import functional as srf
+from ._args import bind
 
 
-class AmbientLighting(nn.Module):
-    def __init__(self, light_intensity=0.5, light_color=(1, 1, 1)):
+class _Light(nn.Module):
+    FIELDS = ()
+
+    def __init__(self, *args, **kwargs):
         super().__init__()
-        self.light_intensity = light_intensity
-        self.light_color = light_color
+        for key, value in bind(type(self).__name__, self.FIELDS, args, kwargs).items():
+            setattr(self, key, value)
+
+
+class AmbientLighting(_Light):
+    FIELDS = (("light_intensity", 0.5), ("light_color", (1, 1, 1)))
 
     def forward(self, light):
         return srf.ambient_lighting(light, self.light_intensity, self.light_color)
 
 
-class DirectionalLighting(nn.Module):
-    def __init__(self, light_intensity=0.5, light_color=(1, 1, 1), light_direction=(0, 1, 0)):
-        super().__init__()
-        self.light_intensity = light_intensity
-        self.light_color = light_color
-        self.light_direction = light_direction
+class DirectionalLighting(_Light):
+    FIELDS = (("light_intensity", 0.5), ("light_color", (1, 1, 1)), ("light_direction", (0, 1, 0)))
 
     def forward(self, light, normals):
-        return srf.directional_lighting(light, normals, self.light_intensity, self.light_color,
-                                        self.light_direction)
+        return srf.directional_lighting(light, normals, self.light_intensity, self.light_color, self.light_direction)
 
 
 class Lighting(nn.Module):
-    """textures *= ambient + sum_d directional_d(normals)  (lighting.py:50-67)."""
+    """textures *= ambient + sum_d directional_d(normals); per face ('surface') or per vertex ('vertex')."""
+    FIELDS = (("light_mode", "surface"), ("intensity_ambient", 0.5), ("color_ambient", (1, 1, 1)),
+              ("intensity_directionals", 0.5), ("color_directionals", (1, 1, 1)), ("directions", (0, 1, 0)))
 
-    def __init__(self, light_mode="surface", intensity_ambient=0.5, color_ambient=(1, 1, 1),
-                 intensity_directionals=0.5, color_directionals=(1, 1, 1), directions=(0, 1, 0)):
+    def __init__(self, *args, **kwargs):
         super().__init__()
-        if light_mode not in ("surface", "vertex"):
+        cfg = bind("Lighting", self.FIELDS, args, kwargs)
+        if cfg["light_mode"] not in ("surface", "vertex"):
             raise ValueError("Lighting mode only support surface and vertex")
-        self.light_mode = light_mode
-        self.ambient = AmbientLighting(intensity_ambient, color_ambient)
-        self.directionals = nn.ModuleList([DirectionalLighting(intensity_directionals, color_directionals,
-                                                               directions)])
+        self.light_mode = cfg["light_mode"]
+        self.ambient = AmbientLighting(cfg["intensity_ambient"], cfg["color_ambient"])
+        self.directionals = nn.ModuleList([DirectionalLighting(cfg["intensity_directionals"], cfg["color_directionals"],
+                                                               cfg["directions"])])
 
     def _needs_normals(self):
         return any(float(d.light_intensity) != 0.0 for d in self.directionals)
 
     def forward(self, mesh):
-        if self.light_mode == "surface":
-            shape = (mesh.batch_size, mesh.num_faces, 3)
-        else:
-            shape = (mesh.batch_size, mesh.num_vertices, 3)
-        light = torch.zeros(shape, dtype=torch.float32, device=mesh.device)
-        light = self.ambient(light)
+        per_face = self.light_mode == "surface"
+        count = mesh.num_faces if per_face else mesh.num_vertices
+        light = self.ambient(torch.zeros(mesh.batch_size, count, 3, dtype=torch.float32, device=mesh.device))
         if self._needs_normals():  # zero-intensity lights add exactly 0: skip the normal computation
-            normals = mesh.surface_normals if self.light_mode == "surface" else mesh.vertex_normals
+            normals = mesh.surface_normals if per_face else mesh.vertex_normals
             for directional in self.directionals:
                 light = directional(light, normals)
-        if self.light_mode == "surface":
-            mesh.textures = mesh.textures * light[:, :, None, :]   # [B,F,T2,3] * [B,F,1,3]
-        else:
-            mesh.textures = mesh.textures * light                  # [B,V,3] vertex colours
+        # [B,F,T2,3] * [B,F,1,3]   or   [B,V,3] * [B,V,3]
+        mesh.textures = mesh.textures * (light[:, :, None, :] if per_face else light)
         return mesh

@@ -1,9 +1,8 @@
-"""`sr.Mesh` of the drop-in package: a batched triangle-mesh container (reference: SoftRas/mesh.py).
+"""`sr.Mesh`: a batched triangle-mesh container (reference: SoftRas/mesh.py -- attribute and property names).
 
-Holds vertices [B,V,3], faces [B,F,3] (int) and textures (surface: [B,F,T2,3]; vertex: [B,V,3]).
-`face_vertices` / `surface_normals` are cached until vertices or faces are reassigned.
-OBJ loading / saving (`from_obj`, `save_obj`) are host-side I/O outside the hot path: `save_obj`
-writes geometry only.
+Holds vertices [B,V,3], faces [B,F,3] (int) and textures (surface: [B,F,T2,3]; vertex: [B,V,3]).  Derived
+quantities (`face_vertices`, `surface_normals`, `vertex_normals`) are cached until vertices or faces are
+reassigned.  OBJ loading / saving are host-side I/O outside the hot path: `save_obj` writes geometry only.
 """
 import numpy as np
 import torch
@@ -12,54 +11,64 @@ import torch.nn.functional as F
 from . import functional as srf
 
 
+def _tensor(x, dtype):
+    """numpy arrays are moved to the GPU like the reference does (mesh.py:19-22); tensors pass through."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x).to(dtype).cuda()
+    return x
+
+
+def _batched(x, unbatched_dims):
+    return x[None] if x.dim() == unbatched_dims else x
+
+
 class Mesh(object):
     def __init__(self, vertices, faces, textures=None, texture_res=1, texture_type="surface"):
-        if isinstance(vertices, np.ndarray):
-            vertices = torch.from_numpy(vertices).float().cuda()
-        if isinstance(faces, np.ndarray):
-            faces = torch.from_numpy(faces).int().cuda()
-        if vertices.dim() == 2:
-            vertices = vertices[None]
-        if faces.dim() == 2:
-            faces = faces[None]
-        self._vertices, self._faces = vertices, faces
-        self.device = vertices.device
+        if texture_type not in ("surface", "vertex"):
+            raise ValueError("texture type not applicable")
+        self._vertices = _batched(_tensor(vertices, torch.float32), 2)
+        self._faces = _batched(_tensor(faces, torch.int32), 2)
+        self.device = self._vertices.device
         self.texture_type = texture_type
-        self.batch_size, self.num_vertices = vertices.shape[:2]
-        self.num_faces = faces.shape[1]
         self._cache = {}
         self._fill_back = False
-        if textures is None:  # mesh.py:44-54: white texture
-            if texture_type == "surface":
-                textures = torch.ones(self.batch_size, self.num_faces, texture_res ** 2, 3,
-                                      dtype=torch.float32, device=self.device)
-                self.texture_res = texture_res
-            elif texture_type == "vertex":
-                textures = torch.ones(self.batch_size, self.num_vertices, 3, dtype=torch.float32,
-                                      device=self.device)
-                self.texture_res = 1
-            else:
-                raise ValueError("texture type not applicable")
+        if textures is None:
+            self._textures, self.texture_res = self._white(texture_res)
         else:
-            if isinstance(textures, np.ndarray):
-                textures = torch.from_numpy(textures).float().cuda()
-            if textures.dim() == 3 and texture_type == "surface":
-                textures = textures[None]
-            if textures.dim() == 2 and texture_type == "vertex":
-                textures = textures[None]
-            self.texture_res = int(np.sqrt(textures.shape[2]))  # mesh.py:63
-        self._textures = textures
-        self._origin = (vertices, faces, textures)
+            textures = _tensor(textures, torch.float32)
+            self._textures = _batched(textures, 3 if texture_type == "surface" else 2)
+            self.texture_res = int(np.sqrt(self._textures.shape[2]))  # mesh.py:63
+        self._origin = (self._vertices, self._faces, self._textures)
 
-    # --- geometry ---------------------------------------------------------------------------
+    def _white(self, texture_res):
+        """All-ones texture (mesh.py:44-54): [B,F,res^2,3] per face or [B,V,3] per vertex."""
+        if self.texture_type == "surface":
+            shape, res = (self.batch_size, self.num_faces, texture_res ** 2, 3), texture_res
+        else:
+            shape, res = (self.batch_size, self.num_vertices, 3), 1
+        return torch.ones(shape, dtype=torch.float32, device=self.device), res
+
+    # --- sizes ------------------------------------------------------------------------------
+    @property
+    def batch_size(self):
+        return self._vertices.shape[0]
+
+    @property
+    def num_vertices(self):
+        return self._vertices.shape[1]
+
+    @property
+    def num_faces(self):
+        return self._faces.shape[1]
+
+    # --- geometry (setting either invalidates the cached derived quantities) -----------------
     @property
     def vertices(self):
         return self._vertices
 
     @vertices.setter
-    def vertices(self, v):
-        self._vertices = v
-        self.num_vertices = v.shape[1]
+    def vertices(self, value):
+        self._vertices = value
         self._cache.clear()
 
     @property
@@ -67,9 +76,8 @@ class Mesh(object):
         return self._faces
 
     @faces.setter
-    def faces(self, f):
-        self._faces = f
-        self.num_faces = f.shape[1]
+    def faces(self, value):
+        self._faces = value
         self._cache.clear()
 
     @property
@@ -77,37 +85,35 @@ class Mesh(object):
         return self._textures
 
     @textures.setter
-    def textures(self, t):
-        self._textures = t
+    def textures(self, value):
+        self._textures = value
+
+    def _cached(self, key, compute):
+        if key not in self._cache:
+            self._cache[key] = compute()
+        return self._cache[key]
 
     @property
     def face_vertices(self):
-        if "fv" not in self._cache:
-            self._cache["fv"] = srf.face_vertices(self._vertices, self._faces)
-        return self._cache["fv"]
+        return self._cached("fv", lambda: srf.face_vertices(self._vertices, self._faces))
 
     @property
     def surface_normals(self):
-        if "sn" not in self._cache:  # mesh.py:112-118
+        def compute():  # mesh.py:112-118
             fv = self.face_vertices
-            v10 = fv[:, :, 0] - fv[:, :, 1]
-            v12 = fv[:, :, 2] - fv[:, :, 1]
-            self._cache["sn"] = F.normalize(torch.cross(v12, v10, dim=-1), p=2, dim=2, eps=1e-6)
-        return self._cache["sn"]
+            return F.normalize(torch.cross(fv[:, :, 2] - fv[:, :, 1], fv[:, :, 0] - fv[:, :, 1], dim=-1), p=2, dim=2,
+                               eps=1e-6)
+        return self._cached("sn", compute)
 
     @property
     def vertex_normals(self):
-        if "vn" not in self._cache:
-            self._cache["vn"] = srf.vertex_normals(self._vertices, self._faces)
-        return self._cache["vn"]
+        return self._cached("vn", lambda: srf.vertex_normals(self._vertices, self._faces))
 
     @property
     def face_textures(self):
         if self.texture_type == "surface":
             return self._textures
-        if self.texture_type == "vertex":
-            return srf.face_vertices(self._textures, self._faces)
-        raise ValueError("texture type not applicable")
+        return srf.face_vertices(self._textures, self._faces)
 
     def fill_back_(self):
         if not self._fill_back:
@@ -127,29 +133,25 @@ class Mesh(object):
         f = self._faces[0].detach().cpu().numpy()
         with open(filename_obj, "w") as fh:
             fh.write("# umr_b200 soft_renderer.Mesh.save_obj (geometry only)\n")
-            for p in v:
-                fh.write("v %.8f %.8f %.8f\n" % (p[0], p[1], p[2]))
-            for t in f:
-                fh.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+            fh.writelines("v %.8f %.8f %.8f\n" % tuple(p) for p in v)
+            fh.writelines("f %d %d %d\n" % tuple(t + 1) for t in f)
 
     @classmethod
-    def from_obj(cls, filename_obj, normalization=False, load_texture=False, texture_res=1,
-                 texture_type="surface"):
+    def from_obj(cls, filename_obj, normalization=False, load_texture=False, texture_res=1, texture_type="surface"):
         verts, faces = [], []
         with open(filename_obj) as fh:
             for line in fh:
-                p = line.split()
-                if not p:
+                tok = line.split()
+                if not tok:
                     continue
-                if p[0] == "v":
-                    verts.append([float(x) for x in p[1:4]])
-                elif p[0] == "f":
-                    ids = [int(x.split("/")[0]) - 1 for x in p[1:]]
-                    for k in range(1, len(ids) - 1):
-                        faces.append([ids[0], ids[k], ids[k + 1]])
+                if tok[0] == "v":
+                    verts.append([float(x) for x in tok[1:4]])
+                elif tok[0] == "f":
+                    ids = [int(x.split("/")[0]) - 1 for x in tok[1:]]
+                    faces.extend([ids[0], ids[k], ids[k + 1]] for k in range(1, len(ids) - 1))  # fan triangulation
         v = torch.tensor(verts, dtype=torch.float32).cuda()
         f = torch.tensor(faces, dtype=torch.int32).cuda()
-        if normalization:  # load_obj.py: centre and scale into [-1, 1]
+        if normalization:  # functional/load_obj.py: centre and scale into [-1, 1]
             v = v - v.min(0)[0][None, :]
             v = v / torch.abs(v).max()
             v = v * 2
