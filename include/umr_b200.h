@@ -116,7 +116,9 @@ typedef struct UmrProjectParams {
 } UmrProjectParams;
 
 /* vertices [B,V,3] f32, cams [B,7] = [s,tx,ty,qw,qx,qy,qz], faces int32 -> face_vertices [B,F,9]
- * (raster space) and light [B,F,3] (NULL or light_enabled == 0 to skip). */
+ * (raster space) and light [B,F,3] (NULL or light_enabled == 0 to skip).  A face index outside [0,V) is never
+ * dereferenced: that face's vertices (and light) become NaN in the forward and it contributes nothing in the
+ * backward (the reference's torch indexing raises a device-side assert, functional/face_vertices.py:22). */
 int umr_project_faces_forward(const float* vertices, const float* cams, const int32_t* faces,
                               float* face_vertices, float* light, const UmrProjectParams* params,
                               void* stream);

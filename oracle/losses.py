@@ -104,3 +104,27 @@ def quat_rotate(X, q):
     X = torch.cat([X[:, :, [0]] * 0, X], dim=-1)
     X_rot = hamilton_product(q, hamilton_product(X, q_conj))
     return X_rot[:, :, 1:4]
+
+
+def dist_chamfer_np(a, b):
+    """nnutils/chamfer_python.py:43-64 with a DEFINED fp32 operation order (numpy float32, one rounding per
+    product / sum, no FMA): |p|^2 = ((p0*p0 + p1*p1) + p2*p2), a.b likewise, P = (|a|^2 + |b|^2) - 2*(a.b).
+    `torch.bmm` leaves the order/fusion of the K=2..3 dot product to the BLAS in use, so the index plane of
+    the torch restatement above is only defined up to near-ties; this one is exact (lowest index on ties)."""
+    import numpy as np
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    D = a.shape[2]
+
+    def sq(p):
+        s = p[..., 0] * p[..., 0]
+        for d in range(1, D):
+            s = s + p[..., d] * p[..., d]
+        return s
+    xx, yy = sq(a), sq(b)
+    zz = a[:, :, None, 0] * b[:, None, :, 0]
+    for d in range(1, D):
+        zz = zz + a[:, :, None, d] * b[:, None, :, d]
+    P = (xx[:, :, None] + yy[:, None, :]) - np.float32(2) * zz
+    assert P.dtype == np.float32
+    return P.min(2), P.min(1), P.argmin(2).astype(np.int32), P.argmin(1).astype(np.int32)

@@ -70,11 +70,20 @@ def test_soft_renderer_forward_matches_oracle(render_type, tex_res):
     ok, msg = rel_report("face_vertices glue", fv.reshape(2, -1, 9), ref_fv.numpy(), 1e-5, 1e-6)
     print(msg)
     assert ok, msg
-    # lighting: default SoftRenderer = ambient 0.8 + directional 0.5 (smr.py:63, renderer.py:57-60)
+    # lighting (a4): default SoftRenderer = ambient 0.8 + directional 0.5 along +y (smr.py:63, renderer.py:57-60).
+    # VALUE check against the closed form of lighting.py:50-57 / mesh.py:112-118 evaluated on the CPU:
+    # light = 0.8 + 0.5 * relu(n_y), n = normalize(cross(v2 - v1, v0 - v1)) of the flipped, pre-transform faces
     if tex is not None:
         assert tx.shape == tex.shape
-        ratio = tx / tex.numpy()
-        assert ratio.min() >= 0.8 - 1e-5 and ratio.max() <= 1.3 + 1e-5
+        import train_step as O
+        _, pre = O.OracleSoftRenderer(64).face_vertices(verts, faces, cams)
+        n = torch.nn.functional.normalize(torch.cross(pre[:, :, 2] - pre[:, :, 1], pre[:, :, 0] - pre[:, :, 1], dim=2),
+                                          p=2, dim=2, eps=1e-6)
+        light = 0.8 + 0.5 * torch.relu(n[:, :, 1])
+        ok, msg = rel_report("lit textures (a4)", tx, (tex * light[:, :, None, None]).numpy(), 2e-5, 1e-6)
+        print(msg)
+        assert ok, msg
+        assert float(light.min()) < 0.81 and float(light.max()) > 1.2   # both the shadowed and the lit side occur
 
 
 def test_project_points_and_bgcolor():

@@ -152,14 +152,45 @@ def test_compat_install_and_overlay(tmp_path):
         (ref / d / "__init__.py").write_text("")
     (ref / "nnutils" / "scops_utils.py").write_text("MARK = 'reference'\n")
     (ref / "nnutils" / "smr.py").write_text("MARK = 'reference smr'\n")
+    (ref / "nnutils" / "geom_utils.py").write_text(
+        "MARK = 'reference geom'\n"
+        "def sample_textures(f, i):\n    return 'reference sampler'\n"
+        "def orthographic_proj_withz(X, cam, offset_z=0.):\n    return 'reference proj'\n"
+        "def rotate_cam(c, a):\n    return 'reference rotate_cam'\n")
+    (ref / "nnutils" / "perceptual_loss.py").write_text(
+        "class PerceptualLoss(object):\n"
+        "    def __call__(self, a, b):\n        return (a - b).abs().mean(dim=(1, 2, 3))\n")
     base = compat.overlay(str(ref), package="UMRT", workdir=str(tmp_path / "ov"))
     try:
         m = importlib.import_module("UMRT.nnutils.smr")
         assert m.SoftRenderer is smr.SoftRenderer            # ours
         assert importlib.import_module("UMRT.nnutils.scops_utils").MARK == "reference"   # theirs, via symlink
         assert importlib.import_module("UMRT.nnutils.chamfer_python").distChamfer is not None
+        # geom_utils: the reference module with the hot functions replaced (one sampling convention)
+        g = importlib.import_module("UMRT.nnutils.geom_utils")
+        from umr_b200.nnutils import geom_utils as ours_geom
+        assert g.MARK == "reference geom" and g.rotate_cam(None, None) == "reference rotate_cam"
+        assert g.orthographic_proj_withz is ours_geom.orthographic_proj_withz and g.quat_rotate is ours_geom.quat_rotate
+        assert g.sample_textures(torch.zeros(1, 1, 1, 1, 2), torch.zeros(1, 1, 2, 2)) == "reference sampler"  # CPU tensors
+        # loss_utils under the overlay: default MultiTextureLoss = perceptual through the REFERENCE's LPIPS module
+        lu = importlib.import_module("UMRT.nnutils.loss_utils")
+        ptl = lu.PerceptualTextureLoss()
+        d = ptl(torch.ones(2, 3, 4, 4), torch.zeros(2, 3, 4, 4), torch.ones(2, 4, 4), torch.ones(2, 4, 4), avg=False)
+        assert d.shape == (2,) and torch.allclose(d, torch.ones(2))
+        assert float(lu.entropy_loss(torch.full((3, 4), 0.25))) == pytest.approx(float(np.log(4.0)))
     finally:
         sys.path.remove(base)
+        for k in [k for k in sys.modules if k.startswith("UMRT")]:
+            del sys.modules[k]
+
+
+def test_perceptual_texture_loss_fails_loudly_without_the_reference_module():
+    """MultiTextureLoss keeps the reference default 'perceptual' and must never fall back to L1
+    silently; without the reference's LPIPS module the constructor raises."""
+    import inspect
+    assert inspect.signature(loss_utils.MultiTextureLoss.__init__).parameters["texture_loss_type"].default == "perceptual"
+    with pytest.raises(NotImplementedError, match="perceptual"):
+        loss_utils.PerceptualTextureLoss()
 
 
 def test_other_camera_modes_and_vertex_normals():

@@ -48,6 +48,43 @@ def test_bit_exact_with_reference_cuda_kernels_built_without_fma(rgb_name, rgb, 
     assert torch.allclose(a.grad, rgf, rtol=1e-3, atol=1e-5 * scale)
 
 
+def _three_way(mod, fv, tex, IS, rgb_name, rgb, check_tex_grad):
+    S = 2 * IS
+    a = fv.clone().requires_grad_(True)
+    t = tex.clone().requires_grad_(True)
+    img, p2f, aggr = raster.soft_rasterize(a, t, IS, aggr_func_rgb=rgb_name, **KW)
+    g = torch.randn(img.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    img.backward(g)
+    colors, rp2f, raggr, finfo = rc.ref_forward(mod, fv, tex, S, rgb)
+    assert torch.equal(img.detach(), F.avg_pool2d(colors, 2, 2)), "pooled RGBA not bit-exact"
+    assert torch.equal(aggr, raggr), "aggregation planes not bit-exact"
+    assert torch.allclose(p2f, rp2f, rtol=1e-4, atol=1e-6)
+    ghi = (g / 4).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    rgf, rgt = rc.ref_backward(mod, fv, tex, colors, finfo, raggr, ghi, S, rgb)
+    scale = float(rgf.abs().max())
+    assert torch.allclose(a.grad, rgf, rtol=1e-3, atol=1e-5 * scale)
+    if check_tex_grad:  # T^2 == 1: the reference's texel-gradient UB (App. B-1) coincides with the intended semantics
+        assert torch.allclose(t.grad, rgt, rtol=1e-3, atol=1e-5 * float(rgt.abs().max()))
+
+
+@pytest.mark.skipif(_mods()[1] is None, reason="baseline/_ref/soft_rasterize_ref_nofma.so not built")
+@pytest.mark.parametrize("rgb_name,rgb", [("softmax", 1), ("hard", 0)])
+def test_bit_exact_at_c2_shape(rgb_name, rgb):
+    """BASELINE config 2 per-image shape: F=1280, 256^2 (S=512), T^2=36, B=2."""
+    fv, tex = rc.scene(2, 6, seed=3)
+    _three_way(_mods()[1], fv, tex, 256, rgb_name, rgb, False)
+
+
+@pytest.mark.skipif(_mods()[1] is None, reason="baseline/_ref/soft_rasterize_ref_nofma.so not built")
+@pytest.mark.parametrize("rgb_name,rgb,tex_res", [("softmax", 1, 1), ("hard", 0, 2)])
+def test_bit_exact_at_c5_shape(rgb_name, rgb, tex_res):
+    """BASELINE config 5 per-image shape: F=5120 (icosphere subdiv 4), 1024^2 (S=2048), B=1 -- the only shape
+    where the cull boxes span several staging pieces and tiles carry long face lists."""
+    fv, tex = rc.scene(1, tex_res, seed=9, subdiv=4)
+    assert fv.shape[1] == 5120
+    _three_way(_mods()[1], fv, tex, 1024, rgb_name, rgb, tex_res == 1)
+
+
 @pytest.mark.skipif(_mods()[0] is None, reason="baseline/_ref/soft_rasterize_ref.so not built")
 def test_face_index_plane_against_reference_as_normally_compiled():
     mod = _mods()[0]

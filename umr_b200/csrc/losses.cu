@@ -161,13 +161,16 @@ __global__ void __launch_bounds__(256) k_chamfer_nn(const float* __restrict__ q,
     const int b = blockIdx.y;
     if (qi >= NQ) return;
     const float* qp = q + ((size_t)b * NQ + qi) * D;
+    // Defined fp32 operation order (never contracted to FMA, whatever the compile flags):
+    //   |p|^2 = ((p0*p0 + p1*p1) + p2*p2),  a.b = ((a0*b0 + a1*b1) + a2*b2),  P = (|q|^2 + |k|^2) - 2*(q.k)
+    // -- chamfer_python.py:58-63 with every product and sum rounded once.  oracle/losses.py::dist_chamfer_np
+    // restates exactly this sequence, so distances AND argmins are bit-exact against it.
     float qv[D];
-    float qq = 0.f;
 #pragma unroll
     for (int d = 0; d < D; ++d) { qv[d] = __ldg(qp + d); }
-    qq = qv[0] * qv[0];
+    float qq = __fmul_rn(qv[0], qv[0]);
 #pragma unroll
-    for (int d = 1; d < D; ++d) qq += qv[d] * qv[d];
+    for (int d = 1; d < D; ++d) qq = __fadd_rn(qq, __fmul_rn(qv[d], qv[d]));
     float best = __int_as_float(0x7f800000);  // +inf
     int bi = 0x7fffffff;
     const float* kb = k + (size_t)b * NK * D;
@@ -175,10 +178,13 @@ __global__ void __launch_bounds__(256) k_chamfer_nn(const float* __restrict__ q,
         float kv[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) kv[d] = __ldg(kb + (size_t)j * D + d);
-        float kk = kv[0] * kv[0], zz = qv[0] * kv[0];
+        float kk = __fmul_rn(kv[0], kv[0]), zz = __fmul_rn(qv[0], kv[0]);
 #pragma unroll
-        for (int d = 1; d < D; ++d) { kk += kv[d] * kv[d]; zz += qv[d] * kv[d]; }
-        const float P = (qq + kk) - 2.f * zz;  // chamfer_python.py:63 expanded form
+        for (int d = 1; d < D; ++d) {
+            kk = __fadd_rn(kk, __fmul_rn(kv[d], kv[d]));
+            zz = __fadd_rn(zz, __fmul_rn(qv[d], kv[d]));
+        }
+        const float P = __fsub_rn(__fadd_rn(qq, kk), __fmul_rn(2.f, zz));  // chamfer_python.py:63 expanded form
         if (P < best) { best = P; bi = j; }
     }
 #pragma unroll

@@ -94,6 +94,14 @@ __global__ void __launch_bounds__(256) k_project_faces(const float* __restrict__
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const int v = __ldg(fi + c);
+        if ((unsigned)v >= (unsigned)V) {
+            // face index outside [0, V): never read out of bounds.  The face becomes NaN (the reference's torch
+            // indexing raises a device-side assert here, face_vertices.py:22); NaN surfaces in every loss downstream.
+            const float nan = __int_as_float(0x7fc00000);
+            out[3 * c] = out[3 * c + 1] = out[3 * c + 2] = nan;
+            pre[3 * c] = pre[3 * c + 1] = pre[3 * c + 2] = nan;
+            continue;
+        }
         const float* p = verts + ((size_t)b * V + v) * 3;
         project(k, pc, __ldg(p), __ldg(p + 1), __ldg(p + 2), out + 3 * c, pre + 3 * c);
     }
@@ -125,6 +133,8 @@ __global__ void __launch_bounds__(256) k_scatter_face_grads(const float* __restr
     int vid[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) vid[c] = __ldg(fi + c);
+    // face with an index outside [0, V) (forward wrote NaN for it): never write out of bounds
+    if ((unsigned)vid[0] >= (unsigned)V || (unsigned)vid[1] >= (unsigned)V || (unsigned)vid[2] >= (unsigned)V) return;
     float g[9];
     const float* gi = gfv + ((size_t)b * F + f) * 9;
     // d/d(pre) of out: x,y scaled by view_scale, z unchanged

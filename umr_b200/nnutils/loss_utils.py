@@ -5,8 +5,11 @@ host-side:
 * no files are read in constructors: `CorrLossChamfer` and `part_matching_loss` take the data the
   reference loads from `scops_path` (`vertices_idx/*.npy`, `semantic_seg.png`) as optional tensors,
   falling back to the reference's file layout when a path is given;
-* the perceptual (LPIPS) branch of `MultiTextureLoss` is outside the hot path (dense CNN): the
-  reference's own L1 alternative `texture_loss_masks` is used (loss_utils.py:289-292);
+* the perceptual (LPIPS) branch of `MultiTextureLoss` is outside the hot path (a dense CNN with
+  downloaded weights): `PerceptualTextureLoss` delegates to the REFERENCE's own `perceptual_loss`
+  module (reachable under `umr_b200.compat.overlay`) and raises loudly when it is not importable --
+  the default stays "perceptual" like the reference (loss_utils.py:279), so the objective never
+  changes silently; pass `texture_loss_type="l1"` for the reference's L1 alternative (:289-292);
 * `TexCycle` builds its visibility mask with a bitmap kernel instead of a per-sample
   `torch.unique` + host sync (loss_utils.py:174-179).
 """
@@ -83,6 +86,48 @@ class edge_regularization(nn.Module):
     def forward(self, pred):
         l2_loss = nn.MSELoss(reduction="mean")
         return l2_loss(pred[:, self.edges[:, 0]], pred[:, self.edges[:, 1]]) * pred.size(-1)
+
+
+class PerceptualTextureLoss(object):
+    """loss_utils.py:128-150.  LPIPS is a dense CNN with downloaded weights -- outside the hot path -- so
+    this is a shim around the REFERENCE's own `nnutils/perceptual_loss.py::PerceptualLoss`, found through
+    the overlay package (`umr_b200.compat.overlay`) or any importable `perceptual_loss` module.  When none
+    is importable the constructor raises: the objective must never silently change to L1."""
+
+    def __init__(self, perceptual_loss=None):
+        if perceptual_loss is None:
+            perceptual_loss = self._find()()
+        self.perceptual_loss = perceptual_loss
+
+    @staticmethod
+    def _find():
+        import importlib
+        import sys
+        tried = []
+        names = [m[:-len("loss_utils")] + "perceptual_loss" for m in list(sys.modules)
+                 if m.endswith(".nnutils.loss_utils") and not m.startswith("umr_b200")]
+        for name in names + ["UMR.nnutils.perceptual_loss", "nnutils.perceptual_loss", "perceptual_loss"]:
+            try:
+                return importlib.import_module(name).PerceptualLoss
+            except Exception as e:  # ImportError, missing LPIPS weights, ...
+                tried.append("%s (%s: %s)" % (name, type(e).__name__, e))
+        raise NotImplementedError(
+            "texture_loss_type='perceptual' needs the reference's LPIPS module (nnutils/perceptual_loss.py + its "
+            "weights), which is outside the B200 hot path and was not importable: %s.  Install umr_b200.compat."
+            "overlay(<reference root>) or pass texture_loss_type='l1'." % "; ".join(tried))
+
+    def __call__(self, img_pred, img_gt, mask_gt, mask_pred=None, avg=True):
+        mask_gt = mask_gt.unsqueeze(1)
+        if mask_pred is not None:
+            dist = self.perceptual_loss(img_pred * mask_pred.unsqueeze(1), img_gt * mask_gt)
+        else:
+            dist = self.perceptual_loss(img_pred * mask_gt, img_gt * mask_gt)
+        return dist.mean() if avg else dist
+
+
+def entropy_loss(A):
+    """loss_utils.py:184-192: mean row entropy of a K x N probability matrix."""
+    return torch.mean(-torch.sum(A * torch.log(A), 1))
 
 
 class TexCycle(nn.Module):
@@ -174,20 +219,21 @@ class MultiMaskLoss(nn.Module):
 
 
 class MultiTextureLoss(nn.Module):
-    """loss_utils.py:277-331 with `texture_loss_type != perceptual` (the L1 alternative, :289-292)
-    and `renderer="smr"`."""
+    """loss_utils.py:277-331, `renderer="smr"`.  `texture_loss_type` defaults to "perceptual" like the
+    reference; that branch needs the reference's LPIPS module (see PerceptualTextureLoss)."""
 
     def __init__(self, samples_per_gpu=32, num_hypo_cams=8, image_size=256, renderer_type="softmax",
-                 texture_loss_type="l1", renderer="smr"):
+                 texture_loss_type="perceptual", renderer="smr"):
         super().__init__()
         if renderer not in "smr":
             raise NotImplementedError("only the SoftRas-based renderer ('smr') is on the hot path")
         self.renderer = SoftRenderer(image_size, renderer_type)
         self.renderer.ambient_light_only()
         self.hard_renderer = SoftRenderer(image_size, "hard")
-        if texture_loss_type in "perceptual":
-            raise NotImplementedError("LPIPS is a dense CNN outside the hot path; use texture_loss_type='l1'")
-        self.texture_loss = texture_loss_masks
+        if texture_loss_type in "perceptual":   # substring test, like the reference (:289)
+            self.texture_loss = PerceptualTextureLoss()   # raises if the reference's LPIPS module is unavailable
+        else:
+            self.texture_loss = texture_loss_masks
         self.texture_cycle_fn = TexCycle(samples_per_gpu)
         self.num_hypo_cams = num_hypo_cams
         self.image_size = image_size

@@ -80,6 +80,9 @@ class NegIouFunction(torch.autograd.Function):
         _need_cuda(predict, target)
         lib = _lib.load()
         B = predict.shape[0]
+        if target.shape[0] != B or target.numel() != predict.numel():
+            raise ValueError("neg_iou_loss: predict %s and target %s must hold the same number of elements per image"
+                             % (tuple(predict.shape), tuple(target.shape)))
         t = target.detach().contiguous().float().view(B, -1)
         N = t.shape[1]
         p, pbs = _batch_view(predict.detach(), N)  # e.g. the alpha plane of the RGBA render, read in place
@@ -125,6 +128,9 @@ class MaskedL1Function(torch.autograd.Function):
         lib = _lib.load()
         B, C, H, W = img_pred.shape
         HW = H * W
+        if tuple(img_gt.shape) != (B, C, H, W) or mask_gt.numel() != B * HW or mask_pred.numel() != B * HW:
+            raise ValueError("texture_loss_masks: img_pred %s, img_gt %s, mask_gt %s, mask_pred %s do not match"
+                             % (tuple(img_pred.shape), tuple(img_gt.shape), tuple(mask_gt.shape), tuple(mask_pred.shape)))
         p, pbs = _batch_view(img_pred.detach(), C * HW)
         mp, mbs = _batch_view(mask_pred.detach(), HW)
         g = img_gt.detach().contiguous().float()

@@ -27,8 +27,40 @@ FUNC_SAMPLE = {"surface": 0, "vertex": 1}
 _profile_sink = None
 
 
+class _EventPair(object):
+    """Two cudaEvents owned by this object: destroyed by the finaliser, so a sink that is dropped without
+    collect_profile() (exception, set_profile_sink(None) and forget) leaks nothing."""
+
+    __slots__ = ("start", "stop")
+
+    def __init__(self):
+        lib = _lib.load()
+        self.start, self.stop = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(lib.umr_event_create(ctypes.byref(self.start)), "umr_event_create")
+        try:
+            _lib.check(lib.umr_event_create(ctypes.byref(self.stop)), "umr_event_create")
+        except Exception:
+            lib.umr_event_destroy(self.start)
+            self.start = ctypes.c_void_p()
+            raise
+
+    def elapsed_ms(self):
+        ms = ctypes.c_float()
+        _lib.check(_lib.load().umr_event_elapsed_ms(self.start, self.stop, ctypes.byref(ms)), "umr_event_elapsed_ms")
+        return float(ms.value)
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for e in (self.start, self.stop):
+                if e is not None and e.value:
+                    lib.umr_event_destroy(e)
+        except Exception:  # interpreter shutdown
+            pass
+
+
 def set_profile_sink(sink):
-    """sink: a list that receives (kind, start_event, stop_event) per raster call, or None to stop."""
+    """sink: a list that receives (kind, _EventPair) per raster call, or None to stop."""
     global _profile_sink
     _profile_sink = sink
 
@@ -36,24 +68,19 @@ def set_profile_sink(sink):
 def _attach_events(params, kind):
     if _profile_sink is None:
         return
-    lib = _lib.load()
-    a, b = ctypes.c_void_p(), ctypes.c_void_p()
-    _lib.check(lib.umr_event_create(ctypes.byref(a)), "umr_event_create")
-    _lib.check(lib.umr_event_create(ctypes.byref(b)), "umr_event_create")
-    params.ev_kernel_start, params.ev_kernel_stop = a.value, b.value
-    _profile_sink.append((kind, a, b))
+    ev = _EventPair()
+    params.ev_kernel_start, params.ev_kernel_stop = ev.start.value, ev.stop.value
+    _profile_sink.append((kind, ev))
 
 
 def collect_profile(sink):
-    """Elapsed milliseconds of every recorded kernel, grouped by kind; destroys the events."""
-    lib = _lib.load()
+    """Elapsed milliseconds of every recorded kernel, grouped by kind; empties the sink (the events are
+    destroyed with their _EventPair objects)."""
     out = {"fwd": [], "bwd": []}
-    for kind, a, b in sink or []:
-        ms = ctypes.c_float()
-        _lib.check(lib.umr_event_elapsed_ms(a, b, ctypes.byref(ms)), "umr_event_elapsed_ms")
-        out[kind].append(float(ms.value))
-        lib.umr_event_destroy(a)
-        lib.umr_event_destroy(b)
+    for kind, ev in sink or []:
+        out[kind].append(ev.elapsed_ms())
+    if sink is not None:
+        del sink[:]
     return out
 
 

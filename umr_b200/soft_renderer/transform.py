@@ -76,6 +76,9 @@ class Transform(nn.Module):
         self.camera_mode = c["camera_mode"]
         builders = {
             "look_at": lambda: LookAt(c["perspective"], c["viewing_angle"], c["viewing_scale"], c["eye"]),
+            # INTENTIONAL DEVIATION: the reference passes (perspective, viewing_angle, viewing_scale,
+            # eye, camera_direction) positionally into Look(camera_direction, perspective, ...) (transform.py:83-85),
+            # shifting every argument by one; the arguments are bound by name here.  `look` is unused by UMR.
             "look": lambda: Look(c["camera_direction"], c["perspective"], c["viewing_angle"], c["viewing_scale"], c["eye"]),
             "projection": lambda: Projection(c["P"], c["dist_coeffs"], c["orig_size"]),
         }
