@@ -61,10 +61,23 @@ typedef struct UmrRasterParams {
      * to time the dominant kernel alone, live, without a profiler. */
     void* ev_kernel_start;
     void* ev_kernel_stop;
+    /* optional PAIR BUFFER (device memory, 256-byte aligned, caller-allocated like every other buffer): when given,
+     * the forward saves one 48-byte record per surviving (pixel, face) pair and the backward streams them instead
+     * of re-deriving the geometry (the role `faces_info`/`soft_colors` play as saved tensors in the reference,
+     * functional/soft_rasterize.py:75).  It must be the SAME memory, untouched, in the matching backward call.
+     * Tiles whose records do not fit are recomputed in the backward -- results are identical, only slower -- so any
+     * size is valid; umr_raster_pair_buffer_bytes() sizes it.  After the forward, the first uint32 of the buffer
+     * holds the number of 32-record blocks the render wanted, the second the number of tiles left unsaved.
+     * NULL / 0: nothing is saved (forward-only renders, generic modes). */
+    void* pair_buffer;
+    uint64_t pair_buffer_bytes;
 } UmrRasterParams;
 
 const char* umr_error_string(int code);
 int umr_version(void);
+/* sizeof() of the parameter structs as compiled into the library (binding self-check). */
+size_t umr_sizeof_raster_params(void);
+size_t umr_sizeof_project_params(void);
 /* Number of kernels this library has launched in this process (all entry points, all threads). */
 uint64_t umr_launch_count(void);
 /* Thin event helpers so callers without a CUDA runtime binding can time on the launch stream. */
@@ -74,7 +87,11 @@ int umr_event_record(void* event, void* stream);
 int umr_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
 
 /* Bytes of scratch `workspace` umr_raster_forward/backward need (256-byte aligned device memory). */
-size_t umr_raster_workspace_bytes(int32_t batch_size, int32_t num_faces);
+size_t umr_raster_workspace_bytes(int32_t batch_size, int32_t num_faces, int32_t image_size, int32_t anti_aliasing);
+/* Bytes of a pair buffer (UmrRasterParams.pair_buffer) holding `capacity_blocks` blocks of 32 pair records
+ * (1540 bytes each) plus the per-tile headers. */
+size_t umr_raster_pair_buffer_bytes(int32_t batch_size, int32_t image_size, int32_t anti_aliasing,
+                                    uint64_t capacity_blocks);
 
 /* Forward.  face_vertices [B,F,9] f32 (x0,y0,z0,x1,...), textures [B,F,T2,3] f32.
  * Outputs (all fully written, no pre-fill needed):

@@ -28,17 +28,23 @@ def test_header_symbols_are_exported():
 
 def test_scalar_entry_points_without_gpu():
     lib = _lib.load()
-    assert lib.umr_version() >= 100
+    assert lib.umr_version() >= 200
     assert lib.umr_error_string(0) == b"ok"
     assert b"not supported" in lib.umr_error_string(-1)
-    assert lib.umr_raster_workspace_bytes(16, 1280) >= 16 * 1280 * (128 + 16 + 16)
-    assert lib.umr_raster_workspace_bytes(0, 5) == 0
+    assert lib.umr_raster_workspace_bytes(16, 1280, 256, 1) >= 16 * 1280 * (128 + 16 + 16) + 16 * 64 * 1280 * 2
+    assert lib.umr_raster_workspace_bytes(0, 5, 64, 1) == 0
+    # pair buffer: 1540 bytes per 32-record block + per-tile headers
+    assert lib.umr_raster_pair_buffer_bytes(2, 64, 1, 1000) >= 1000 * 1540 + 2 * 64 * 4
+    assert lib.umr_raster_pair_buffer_bytes(0, 64, 1, 10) == 0
     assert lib.umr_launch_count() >= 0
 
 
 def test_params_struct_matches_header():
     p = _lib.UmrRasterParams()
-    assert ctypes.sizeof(p) == 5 * 4 + 6 * 4 + 5 * 4 + 3 * 4 + 4 + 2 * 8  # 4 bytes padding before the pointers
+    assert ctypes.sizeof(p) == 5 * 4 + 6 * 4 + 5 * 4 + 3 * 4 + 4 + 2 * 8 + 8 + 8  # 4 bytes padding before the pointers
+    lib = _lib.load()
+    assert lib.umr_sizeof_raster_params() == ctypes.sizeof(p)
+    assert lib.umr_sizeof_project_params() == ctypes.sizeof(_lib.UmrProjectParams())
 
 
 def test_missing_library_fails_loudly(monkeypatch):

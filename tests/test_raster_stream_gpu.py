@@ -1,0 +1,61 @@
+"""Round-2 raster pipeline (csrc/raster_stream.cuh): the backward that STREAMS the forward's saved pair records
+must agree with (a) the CPU oracle, (b) the round-1 recompute backward (no pair buffer), and (c) itself when the
+pair buffer is too small and some / all tiles fall back to the recompute kernel."""
+import numpy as np
+import pytest
+import torch
+
+from umr_b200 import raster
+from util import rel_report, scene
+from test_raster_gpu import UMR, run_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(fv, tex, image_size, rgb, g, cand_per_pixel):
+    old = raster.PAIR_CAND_PER_PIXEL
+    raster.PAIR_CAND_PER_PIXEL = cand_per_pixel
+    try:
+        tfv = torch.from_numpy(fv).to(DEV).requires_grad_(True)
+        ttex = torch.from_numpy(tex).to(DEV).requires_grad_(True)
+        img, p2f, aggr = raster.soft_rasterize(tfv, ttex, image_size, aggr_func_rgb=rgb, anti_aliasing=True, **UMR)
+        stats = None
+        saved = img.grad_fn.saved_tensors
+        if len(saved) == 5:
+            stats = saved[4][:8].view(torch.int32).cpu().tolist()  # [blocks wanted, tiles unsaved]
+        img.backward(torch.from_numpy(g).to(DEV))
+        torch.cuda.synchronize()
+        return dict(images=img.detach().cpu().numpy(), grad_faces=tfv.grad.cpu().numpy(), grad_tex=ttex.grad.cpu().numpy(),
+                    stats=stats)
+    finally:
+        raster.PAIR_CAND_PER_PIXEL = old
+
+
+@pytest.mark.parametrize("rgb", ["softmax", "hard"])
+@pytest.mark.parametrize("B,subdiv,tex_res,image_size", [(2, 3, 3, 64), (1, 3, 6, 128), (1, 2, 2, 37)])
+def test_streamed_backward_matches_recompute_and_oracle(rgb, B, subdiv, tex_res, image_size):
+    fv, tex = scene(B, subdiv, tex_res, seed=31 + image_size)
+    g = np.random.default_rng(5).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
+    ref = run_oracle(fv, tex, image_size, True, rgb, g)
+    full = _run(fv, tex, image_size, rgb, g, 8.0)     # everything saved
+    none = _run(fv, tex, image_size, rgb, g, 0.0)     # no pair buffer: recompute backward
+    part = _run(fv, tex, image_size, rgb, g, 0.7)     # buffer too small: some tiles saved, the rest recomputed
+    tiny = _run(fv, tex, image_size, rgb, g, 1e-4)    # nothing fits
+    assert full["stats"][1] == 0 and full["stats"][0] > 0, full["stats"]
+    assert none["stats"] is None
+    assert part["stats"][1] > 0, "the partial-capacity case must leave tiles unsaved: %s" % (part["stats"],)
+    assert tiny["stats"][1] > 0
+    at = 1e-6 * float(np.abs(ref["grad_faces"]).max() + 1e-30) + 1e-7
+    for name, got in (("streamed", full), ("recompute", none), ("partial", part), ("tiny", tiny)):
+        assert np.array_equal(got["images"], full["images"])
+        for k, a in (("grad_faces", at), ("grad_tex", 1e-6)):
+            ok, msg = rel_report("%s %s" % (name, k), got[k], ref[k], 1e-4, a)
+            print(msg)
+            assert ok, msg
+
+
+def test_forward_only_render_needs_no_pair_buffer():
+    fv, tex = scene(1, 2, 1, seed=2)
+    img, _, _ = raster.soft_rasterize(torch.from_numpy(fv).to(DEV), torch.from_numpy(tex).to(DEV), 32, anti_aliasing=True, **UMR)
+    assert img.grad_fn is None

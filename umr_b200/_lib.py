@@ -22,7 +22,8 @@ class UmrRasterParams(ctypes.Structure):
                 ("func_id_dist", ctypes.c_int32), ("func_id_rgb", ctypes.c_int32),
                 ("func_id_alpha", ctypes.c_int32), ("texture_sample_type", ctypes.c_int32),
                 ("double_side", ctypes.c_int32), ("background_color", ctypes.c_float * 3),
-                ("ev_kernel_start", ctypes.c_void_p), ("ev_kernel_stop", ctypes.c_void_p)]
+                ("ev_kernel_start", ctypes.c_void_p), ("ev_kernel_stop", ctypes.c_void_p),
+                ("pair_buffer", ctypes.c_void_p), ("pair_buffer_bytes", ctypes.c_uint64)]
 
 
 class UmrProjectParams(ctypes.Structure):
@@ -39,12 +40,15 @@ EXPORTS = {
     # name: (restype, argtypes)
     "umr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "umr_version": (ctypes.c_int, []),
+    "umr_sizeof_raster_params": (ctypes.c_size_t, []),
+    "umr_sizeof_project_params": (ctypes.c_size_t, []),
     "umr_launch_count": (ctypes.c_uint64, []),
     "umr_event_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
     "umr_event_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "umr_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "umr_event_elapsed_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
-    "umr_raster_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "umr_raster_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 4),
+    "umr_raster_pair_buffer_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 3 + [ctypes.c_uint64]),
     "umr_raster_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
                                                         ctypes.c_void_p]),
     "umr_raster_backward": (ctypes.c_int, [c_f32p] * 7 + [ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
@@ -92,6 +96,10 @@ def load():
                 fn = getattr(lib, name)  # AttributeError if the symbol is missing
                 fn.restype = res
                 fn.argtypes = args
+            if (lib.umr_sizeof_raster_params() != ctypes.sizeof(UmrRasterParams)
+                    or lib.umr_sizeof_project_params() != ctypes.sizeof(UmrProjectParams)):
+                raise UmrLibraryError("libumr_b200.so was built from a different include/umr_b200.h than this binding "
+                                      "(parameter struct sizes differ): rebuild with `python -m umr_b200.build --force`")
             _lib = lib
     return _lib
 

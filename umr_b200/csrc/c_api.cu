@@ -15,7 +15,9 @@ extern "C" const char* umr_error_string(int code) {
     return "unknown error";
 }
 
-extern "C" int umr_version(void) { return 100; }
+extern "C" int umr_version(void) { return 200; }  // 200: round-2 ABI (pair buffer, workspace size takes the image size)
+extern "C" size_t umr_sizeof_raster_params(void) { return sizeof(UmrRasterParams); }
+extern "C" size_t umr_sizeof_project_params(void) { return sizeof(UmrProjectParams); }
 
 #include <atomic>
 namespace umr { std::atomic<unsigned long long> g_launches{0}; }

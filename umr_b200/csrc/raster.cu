@@ -57,17 +57,22 @@ constexpr int R_FLG = 28;  // 1 : bit0..2 obtuse corner, bit3 front-facing
 // 29..31 pad
 
 struct WorkspaceLayout {
-    size_t rec_off, box_off, p2f_off, ubox_off, total;
+    size_t rec_off, box_off, p2f_off, ubox_off, ccount_off, clist_off, total;
 };
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-inline WorkspaceLayout ws_layout(int B, int F) {
+constexpr int COARSE_BIN = 64;  // == CB in raster_stream.cuh
+// S = raster side (0: no coarse-bin lists, e.g. the generic-mode kernels)
+inline WorkspaceLayout ws_layout(int B, int F, int S) {
     WorkspaceLayout L;
     const size_t n = (size_t)B * F;
+    const size_t ncb = (size_t)(S + COARSE_BIN - 1) / COARSE_BIN;
     L.rec_off = 0;
     L.box_off = align256(n * REC_F * sizeof(float));
     L.p2f_off = L.box_off + align256(n * sizeof(float4));
     L.ubox_off = L.p2f_off + align256(n * 4 * sizeof(float));
-    L.total = L.ubox_off + align256((size_t)B * 4 * sizeof(uint32_t));
+    L.ccount_off = L.ubox_off + align256((size_t)B * 4 * sizeof(uint32_t));
+    L.clist_off = L.ccount_off + align256((size_t)B * ncb * ncb * sizeof(int));
+    L.total = L.clist_off + align256((size_t)B * ncb * ncb * F * sizeof(uint16_t));
     return L;
 }
 
@@ -1106,7 +1111,13 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
                                                              const float* __restrict__ grad_images,
                                                              float* __restrict__ grad_faces,
                                                              float* __restrict__ grad_tex,
-                                                             const uint32_t* __restrict__ ubox, Consts K) {
+                                                             const uint32_t* __restrict__ ubox, Consts K,
+                                                             const int32_t* __restrict__ tile_head) {
+    // With a pair buffer this kernel is only the FALLBACK for tiles the forward could not save (tile_head ==
+    // TILE_UNSAVED, -2); every other tile is streamed by k_raster_bwd2 (raster_stream.cuh).
+    if (tile_head != nullptr &&
+        __ldg(tile_head + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) != -2)
+        return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
     float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
@@ -1283,14 +1294,40 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
 
 }  // namespace umr
 
+#include "raster_stream.cuh"
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
 using namespace umr;
 
-extern "C" size_t umr_raster_workspace_bytes(int32_t B, int32_t F) {
-    if (B <= 0 || F <= 0) return 0;
-    return ws_layout(B, F).total;
+extern "C" size_t umr_raster_workspace_bytes(int32_t B, int32_t F, int32_t image_size, int32_t anti_aliasing) {
+    if (B <= 0 || F <= 0 || image_size <= 0) return 0;
+    return ws_layout(B, F, image_size * (anti_aliasing ? 2 : 1)).total;
+}
+
+extern "C" size_t umr_raster_pair_buffer_bytes(int32_t B, int32_t image_size, int32_t anti_aliasing,
+                                               uint64_t capacity_blocks) {
+    if (B <= 0 || image_size <= 0) return 0;
+    return pair_layout(B, image_size * (anti_aliasing ? 2 : 1), (size_t)capacity_blocks).total + 1024;
+}
+
+// device pointers into the caller's pair buffer (cap == 0: no saving)
+static PairBuf make_pairbuf(const UmrRasterParams* p, int S) {
+    PairBuf pb;
+    pb.ctrl = nullptr; pb.tile_head = nullptr; pb.blk_hdr = nullptr; pb.recs = nullptr; pb.cap = 0;
+    if (!p->pair_buffer || p->pair_buffer_bytes == 0 || ((uintptr_t)p->pair_buffer & 255) != 0) return pb;
+    size_t cap = pair_capacity(p->batch_size, S, (size_t)p->pair_buffer_bytes);
+    if (cap > 0x7fff0000u) cap = 0x7fff0000u;
+    if (cap < 4) return pb;
+    const PairBufLayout L = pair_layout(p->batch_size, S, cap);
+    char* base = (char*)p->pair_buffer;
+    pb.ctrl = (uint32_t*)(base + L.ctrl_off);
+    pb.tile_head = (int32_t*)(base + L.head_off);
+    pb.blk_hdr = (uint32_t*)(base + L.hdr_off);
+    pb.recs = (float4*)(base + L.rec_off);
+    pb.cap = (uint32_t)cap;
+    return pb;
 }
 
 static int check_params(const UmrRasterParams* p) {
@@ -1352,7 +1389,6 @@ static int ensure_smem_attrs() {
     e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
                              optin - (int)fa.sharedSizeBytes);                                       \
     if (e != cudaSuccess) return (int)e;
-    UMR_SET((k_raster_fwd<0, false>)) UMR_SET((k_raster_fwd<1, false>))
     UMR_SET((k_raster_fwd<0, true>)) UMR_SET((k_raster_fwd<1, true>))
     UMR_SET((k_raster_bwd<0, false, false>)) UMR_SET((k_raster_bwd<0, true, false>))
     UMR_SET((k_raster_bwd<1, false, false>)) UMR_SET((k_raster_bwd<1, true, false>))
@@ -1381,12 +1417,14 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     Consts K = make_consts(p);
     if (!K.aa && soft_colors == nullptr) soft_colors = images;
     K.vec_store = (K.aa && (K.S % 8) == 0 && (((uintptr_t)images | (uintptr_t)soft_colors | (uintptr_t)aggrs_info) & 15) == 0) ? 1 : 0;
-    const WorkspaceLayout L = ws_layout(B, F);
+    const WorkspaceLayout L = ws_layout(B, F, K.S);
     char* ws = (char*)workspace;
     float* rec = (float*)(ws + L.rec_off);
     float4* box = (float4*)(ws + L.box_off);
     float* p2f_acc = (float*)(ws + L.p2f_off);
     uint32_t* ubox = (uint32_t*)(ws + L.ubox_off);
+    int* ccount = (int*)(ws + L.ccount_off);
+    uint16_t* clist = (uint16_t*)(ws + L.clist_off);
     const int n = B * F;
     const float r = sqrtf(K.thr);  // kernel.cu:355 sqrt(threshold) in float
     {
@@ -1403,21 +1441,39 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     }
     const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
     const size_t smem = raster_dyn_smem(F);
-    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
-    count_launch();
     const bool gen = is_generic(p);
     float* pacc = (softmax && want_p2f) ? p2f_acc : nullptr;
+    if (!gen) {
+        // round-2 pipeline: coarse bins -> pair-parallel forward (saves pair records when a pair buffer is given)
+        const int ncb = (K.S + CB - 1) / CB;
+        const PairBuf pb = make_pairbuf(p, K.S);
+        if (pb.cap > 0) {
+            cudaError_t e = cudaMemsetAsync(pb.ctrl, 0, 16, stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+        count_launch(2);
+        k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
+        if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
+        if (softmax)
+            k_raster_fwd2<1><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc,
+                                                       ubox, K, p->eps, p->background_color[0], p->background_color[1],
+                                                       p->background_color[2], pb, ncb);
+        else
+            k_raster_fwd2<0><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc,
+                                                       ubox, K, p->eps, p->background_color[0], p->background_color[1],
+                                                       p->background_color[2], pb, ncb);
+        if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
+    } else {
+    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
+    count_launch();
 #define UMR_LAUNCH_FWD(RGBM, GENM)                                                                           \
     k_raster_fwd<RGBM, GENM><<<grid, CTA, smem, stream>>>(rec, box, textures, images, soft_colors, aggrs_info, \
                                                           pacc, ubox, K, p->eps, p->background_color[0],      \
                                                           p->background_color[1], p->background_color[2])
-    if (softmax) {
-        if (gen) UMR_LAUNCH_FWD(1, true); else UMR_LAUNCH_FWD(1, false);
-    } else {
-        if (gen) UMR_LAUNCH_FWD(0, true); else UMR_LAUNCH_FWD(0, false);
-    }
+    if (softmax) UMR_LAUNCH_FWD(1, true); else UMR_LAUNCH_FWD(0, true);
 #undef UMR_LAUNCH_FWD
     if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
+    }
     if (want_p2f) {
         if (softmax) {
             count_launch();
@@ -1445,7 +1501,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     if (rc) return rc;
     const int B = p->batch_size, F = p->num_faces;
     const Consts K = make_consts(p);
-    const WorkspaceLayout L = ws_layout(B, F);
+    const WorkspaceLayout L = ws_layout(B, F, K.S);
     char* ws = (char*)workspace;
     float* rec = (float*)(ws + L.rec_off);
     float4* box = (float4*)(ws + L.box_off);
@@ -1475,14 +1531,26 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         if (gen)                                                                                              \
             k_raster_bwd<RGBM, TG, true><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                                       grad_images, grad_faces, grad_textures, ubox, K); \
-        else if (use_pairs)                                                                                   \
+        else if (use_pairs) {                                                                                 \
+            if (pb.cap > 0) {                                                                                 \
+                count_launch();                                                                               \
+                k_raster_bwd2<RGBM, TG><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images,  \
+                                                                        grad_faces, grad_textures, K, pb);    \
+            }                                                                                                 \
             k_raster_bwd_pairs<RGBM, TG><<<grid_pairs, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
-                                                                      grad_images, grad_faces, grad_textures, ubox, K); \
+                                                                      grad_images, grad_faces, grad_textures, ubox, K,  \
+                                                                      pb.cap > 0 ? pb.tile_head : nullptr);   \
+        }                                                                                                     \
         else                                                                                                  \
             k_raster_bwd<RGBM, TG, false><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                                        grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
     const bool gen = is_generic(p);
+    static const bool no_stream = [] {  // UMR_BWD_IMPL=recompute ignores the pair buffer (A/B testing)
+        const char* e = getenv("UMR_BWD_IMPL");
+        return e && e[0] == 'r' && e[1] == 'e' && e[2] == 'c';
+    }();
+    const PairBuf pb = (gen || no_stream) ? PairBuf{nullptr, nullptr, nullptr, nullptr, 0u} : make_pairbuf(p, K.S);
     const dim3 grid_pairs((K.S + PT - 1) / PT, (K.S + PT - 1) / PT, B);
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();

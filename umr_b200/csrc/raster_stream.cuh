@@ -1,0 +1,652 @@
+// raster_stream.cuh -- round-2 raster pipeline: coarse binning, pair-parallel forward that SAVES one
+// compact record per surviving (pixel, face) pair, and a streaming backward that consumes them.
+// Included by raster.cu (same translation unit: -fmad=false, same exact-twin arithmetic helpers).
+//
+// Why (profiles/r01_raster_v6_bwd_pairs_ncu_summary.txt): the round-1 backward
+// re-derived fragment() (~13 IEEE divisions + a double sigmoid) for every pair the forward had already
+// evaluated, behind 3 CTA barriers per 32-face chunk, at 0.9 % of the HBM roofline with DRAM 99 % idle;
+// and every tile CTA re-scanned all F cull boxes in both passes.  Now:
+//   k_bin_coarse     one CTA per 64x64-pixel bin scans the image's F cull boxes ONCE (TMA-staged, ordered
+//                    ballot compaction) -> ascending face list per bin.  Tiles scan their bin's list
+//                    (~100-200 entries) instead of F (1280 / 5120).
+//   k_raster_fwd2    one CTA per 16x16 tile.  Per sub-chunk of faces:
+//                      phase A (pair-parallel, all lanes busy): every candidate (pixel, face) of the faces'
+//                        cull-box rectangles runs the exact-twin fragment(); survivors leave D / depth /
+//                        texel id in a shared slot AND, when a pair buffer is given, one 48-byte record in HBM
+//                        (32-candidate blocks, survivors compacted to the block front, block-SoA so a warp
+//                        writes three fully coalesced 512-byte lines);
+//                      phase B (pixel-parallel): each pixel walks the faces in ascending index (ordered
+//                        semantics: p2f prefix-max weights kernel.cu:421-430, hard z-buffer strict '<' :409)
+//                        and folds its slots into alpha / softmax / colour; p2f by warp-shuffle reduction.
+//   k_raster_bwd2    one CTA per tile streams the tile's blocks: no cull boxes, no fragment(), no barrier
+//                    after the per-pixel inputs are staged; a warp owns a contiguous block range, so the 9
+//                    vertex gradients are accumulated privately and flushed (shuffle reduce + 9 RED) once per
+//                    (warp, face run).
+// Tiles whose blocks do not fit the caller's pair buffer are marked UNSAVED and take the round-1 recompute
+// kernel (k_raster_bwd_pairs) -- results are identical either way (tests/test_raster_stream_gpu.py).
+#pragma once
+
+namespace umr {
+
+constexpr int CB = 64;             // coarse bin side in pixels (4 x 4 tiles)
+constexpr int LCAP = 512;          // coarse-list window == longest tile-list segment held in shared memory
+constexpr int SUB_BLOCKS = 64;     // 32-candidate blocks per sub-chunk
+constexpr int SLOTS = SUB_BLOCKS * 32;
+constexpr uint32_t SEG_NONE = 0xffffffffu;
+constexpr int32_t TILE_EMPTY = -1, TILE_UNSAVED = -2;
+constexpr int BLK_F4 = 96;         // float4 per block: 3 planes x 32 records
+
+// slot / record flag bits
+constexpr uint32_t SL_VALID = 1u << 31, SL_ZV = 1u << 30, SL_FRONT = 1u << 29, SL_INS = 1u << 28, SL_TIX = 0xffffu;
+
+struct PairBuf {
+    uint32_t* ctrl;      // [0] block cursor (== blocks wanted, may exceed cap), [1] tiles left unsaved
+    int32_t* tile_head;  // [B * tiles]: first segment (block index), TILE_EMPTY or TILE_UNSAVED
+    uint32_t* blk_hdr;   // [cap]: per block  face | count << 16 ; per segment  [base] = #blocks, [base+1] = next
+    float4* recs;        // [cap][3][32]
+    uint32_t cap;        // blocks
+};
+
+struct PairBufLayout {
+    size_t ctrl_off, head_off, hdr_off, rec_off, total;
+};
+inline PairBufLayout pair_layout(int B, int S, size_t cap_blocks) {
+    PairBufLayout L;
+    const size_t nt = (size_t)((S + TILE - 1) / TILE) * ((S + TILE - 1) / TILE) * B;
+    L.ctrl_off = 0;
+    L.head_off = 256;
+    L.hdr_off = L.head_off + align256(nt * sizeof(int32_t));
+    L.rec_off = L.hdr_off + align256(cap_blocks * sizeof(uint32_t));
+    L.total = L.rec_off + cap_blocks * (size_t)BLK_F4 * sizeof(float4);
+    return L;
+}
+// largest capacity (blocks) that fits `bytes`
+inline size_t pair_capacity(int B, int S, size_t bytes) {
+    const PairBufLayout z = pair_layout(B, S, 0);
+    if (bytes <= z.total + 512) return 0;
+    size_t cap = (bytes - z.total - 512) / ((size_t)BLK_F4 * sizeof(float4) + sizeof(uint32_t));
+    while (cap > 0 && pair_layout(B, S, cap).total > bytes) --cap;
+    return cap;
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse binning: grid (ncb, ncb, B).  clist[(b, cy, cx)][F] u16, ccount[(b, cy, cx)]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA) k_bin_coarse(const float4* __restrict__ box_all, const uint32_t* __restrict__ ubox,
+                                                    uint16_t* __restrict__ clist, int* __restrict__ ccount, int F, int S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* s_box = reinterpret_cast<float4*>(smem_raw);
+    __shared__ uint64_t s_bar;
+    __shared__ int s_warp_cnt[NWARP];
+    __shared__ float s_ext[4];
+    const int b = blockIdx.z;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    tile_extents(S, s_ext, CB);
+    __syncthreads();
+    const size_t cidx = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    int n = 0;
+    if (!tile_outside_union(ubox, b, s_ext))
+        n = build_tile_list(box_all + (size_t)b * F, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, clist + cidx * F,
+                            s_warp_cnt, &s_bar);
+    if (threadIdx.x == 0) ccount[cidx] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int RGB>
+__global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
+                                                        const uint16_t* __restrict__ clist, const int* __restrict__ ccount,
+                                                        const float* __restrict__ textures, float* __restrict__ images,
+                                                        float* __restrict__ colors_hi, float* __restrict__ aggrs,
+                                                        float* __restrict__ p2f_acc, const uint32_t* __restrict__ ubox,
+                                                        Consts K, float eps, float bg0, float bg1, float bg2, PairBuf pb,
+                                                        int ncb) {
+    __shared__ __align__(128) float s_rec[NSTAGE * CHUNK * REC_F];  // 8 KB; reused by the store epilogue
+    __shared__ float s_sD[SLOTS], s_sZ[SLOTS];
+    __shared__ uint32_t s_sT[SLOTS];
+    __shared__ uint16_t s_list[LCAP];
+    __shared__ uint32_t s_geo[LCAP];
+    __shared__ uint32_t s_boff[LCAP + 1];
+    __shared__ float s_xp[TILE], s_yp[TILE], s_ext[4];
+    __shared__ int s_warp_cnt[NWARP];
+    __shared__ uint32_t s_warp_blk[NWARP];
+    __shared__ uint32_t s_segbase;  // first record block of the current segment (valid while s_save)
+    __shared__ int s_save;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int S = K.S, F = K.F;
+    const PixelMap pm = map_pixel(S);
+    const int px = pm.px, py = pm.py;
+    const bool live = pm.live;
+    const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+    const int lcol = px - tx0, lrow = py - ty0;       // pixel position inside the tile
+    const int ncol = min(TILE, S - tx0), nrow = min(TILE, S - ty0);
+    const int bx0 = (warp & 1) * 8, by0 = (warp >> 1) * 4;  // this warp's 8x4 pixel block inside the tile
+
+    tile_extents(S, s_ext);
+    if (tid < TILE) s_xp[tid] = pixel_coord(tx0 + tid, S);
+    else if (tid < 2 * TILE) s_yp[tid - TILE] = pixel_coord(S - 1 - (ty0 + tid - TILE), S);
+    if (tid == 0) s_save = pb.cap > 0 ? 1 : 0;
+    __syncthreads();
+
+    const size_t tile_id = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const size_t cidx = ((size_t)b * ncb + (ty0 / CB)) * ncb + (tx0 / CB);
+    const int nc = tile_outside_union(ubox, b, s_ext) ? 0 : __ldg(ccount + cidx);
+    const uint16_t* cl = clist + cidx * F;
+    const float4* box = box_all + (size_t)b * F;
+    const float* rec_img = rec_all + (size_t)b * F * REC_F;
+    const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
+    const float ext0 = s_ext[0], ext1 = s_ext[1], ext2 = s_ext[2], ext3 = s_ext[3];
+
+    // pixel state (kernel.cu:335-348)
+    float acc_a = 1.f;
+    float ssum = expf(eps / K.gamma);
+    float smax = eps;
+    float c0, c1, c2;
+    if (RGB == 1) { c0 = bg0 * ssum; c1 = bg1 * ssum; c2 = bg2 * ssum; }
+    else { c0 = bg0; c1 = bg1; c2 = bg2; }
+    float zmin = 10000000.f;
+    int fid = -1;
+    // torch-1.1 affine_grid (align_corners=True) coordinates of this pixel: linspace(-1, 1, S)
+    const float gstep = 2.f / (float)(S - 1);
+    const float gx = (px * 2 < S) ? (-1.f + gstep * px) : (1.f - gstep * (S - 1 - px));
+    const float gy = (py * 2 < S) ? (-1.f + gstep * py) : (1.f - gstep * (S - 1 - py));
+
+    int32_t head = TILE_EMPTY;     // meaningful in thread 0
+    uint32_t prev_seg = SEG_NONE;  // meaningful in thread 0
+    const uint32_t lt = (1u << lane) - 1u;
+
+    for (int w0 = 0; w0 < nc; w0 += LCAP) {
+        // ---- tile-list segment: ordered compaction of this window's coarse entries that touch the tile ------
+        const int nwin = min(LCAP, nc - w0);
+        uint32_t masks[LCAP / CTA], geos[LCAP / CTA];
+        uint16_t fids[LCAP / CTA];
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < LCAP / CTA; ++r) {
+            const int i = warp * (LCAP / NWARP) + r * 32 + lane;
+            bool hit = false;
+            uint32_t geo = 0;
+            uint16_t f = 0;
+            if (i < nwin) {
+                f = __ldg(cl + w0 + i);
+                const float4 bb = __ldg(box + f);
+                hit = !(ext0 > bb.y || ext1 < bb.x || ext2 > bb.w || ext3 < bb.z);
+                if (hit) {
+                    // rectangle of tile pixels passing the per-pixel cull test !(xp > hi || xp < lo || ...) (kernel.cu:32-38);
+                    // pixel-centre coordinates are monotone, so it is [c_lo, c_hi) x [r_lo, r_hi).  Counting with the SAME
+                    // comparisons keeps NaN boxes "never culled", like the per-pixel form.
+                    int c_lo = 0, c_gt = 0, r_lo = 0, r_lt = 0;
+#pragma unroll
+                    for (int q = 0; q < TILE; ++q) {
+                        const float x = s_xp[q], y = s_yp[q];
+                        c_lo += (q < ncol && x < bb.x) ? 1 : 0;
+                        c_gt += (q < ncol && x > bb.y) ? 1 : 0;
+                        r_lo += (q < nrow && y > bb.w) ? 1 : 0;
+                        r_lt += (q < nrow && y < bb.z) ? 1 : 0;
+                    }
+                    const int w = max(0, ncol - c_gt - c_lo), h = max(0, nrow - r_lt - r_lo);
+                    geo = (uint32_t)c_lo | ((uint32_t)w << 4) | ((uint32_t)r_lo << 9) | ((uint32_t)h << 13);
+                }
+            }
+            masks[r] = __ballot_sync(0xffffffffu, hit);
+            geos[r] = geo;
+            fids[r] = f;
+            cnt += __popc(masks[r]);
+        }
+        if (lane == 0) s_warp_cnt[warp] = cnt;
+        __syncthreads();
+        int off = 0, n = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) {
+            const int c = s_warp_cnt[w];
+            if (w < warp) off += c;
+            n += c;
+        }
+#pragma unroll
+        for (int r = 0; r < LCAP / CTA; ++r) {
+            if ((masks[r] >> lane) & 1u) {
+                const int pos = off + __popc(masks[r] & lt);
+                s_list[pos] = fids[r];
+                s_geo[pos] = geos[r];
+            }
+            off += __popc(masks[r]);
+        }
+        __syncthreads();  // list + geo visible; s_warp_cnt reusable
+        if (n == 0) continue;  // uniform
+
+        // ---- block offsets: exclusive prefix of ceil(w*h / 32) over the segment (2 entries per thread) ---------
+        {
+            uint32_t v0 = 0, v1 = 0;
+            const int i0 = 2 * tid, i1 = 2 * tid + 1;
+            if (i0 < n) { const uint32_t g = s_geo[i0]; v0 = (((g >> 4) & 31u) * ((g >> 13) & 31u) + 31u) >> 5; }
+            if (i1 < n) { const uint32_t g = s_geo[i1]; v1 = (((g >> 4) & 31u) * ((g >> 13) & 31u) + 31u) >> 5; }
+            uint32_t incl = v0 + v1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) s_warp_blk[warp] = incl;
+            __syncthreads();
+            uint32_t base = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) {
+                const uint32_t c = s_warp_blk[w];
+                base += (w < warp) ? c : 0u;
+                total += c;
+            }
+            const uint32_t excl = base + incl - (v0 + v1);
+            if (i0 < n) s_boff[i0] = excl;
+            if (i1 < n) s_boff[i1] = excl + v0;
+            if (tid == 0) s_boff[n] = total;
+        }
+        __syncthreads();
+        const uint32_t NBw = s_boff[n];
+
+        // ---- reserve the segment's blocks in the pair buffer --------------------------------------------------
+        if (tid == 0 && s_save && NBw > 0) {
+            const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
+            if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
+                s_save = 0;  // does not fit: the whole tile falls back to the recompute backward
+                head = TILE_UNSAVED;
+                atomicAdd(pb.ctrl + 1, 1u);
+            } else {
+                pb.blk_hdr[base] = NBw;
+                pb.blk_hdr[base + 1] = SEG_NONE;
+                if (prev_seg == SEG_NONE) head = (int32_t)base;
+                else pb.blk_hdr[prev_seg + 1] = base;
+                prev_seg = base;
+                s_segbase = base + 2u;
+            }
+        }
+        // (made visible by the barrier inside the chunk loop before phase A)
+
+        const int nchunk = (n + CHUNK - 1) / CHUNK;
+        issue_chunk(rec_img, s_list, n, 0, s_rec);
+        issue_chunk(rec_img, s_list, n, 1, s_rec);
+        for (int c = 0; c < nchunk; ++c) {
+            const int st = c % NSTAGE;
+            const int cbeg = c * CHUNK, cend = min(n, cbeg + CHUNK);
+            cp_async_wait<1>();
+            __syncthreads();  // chunk c landed for every thread; s_save / s_segbase visible
+            const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
+            const bool save = s_save != 0;
+            const uint32_t segbase = s_segbase;
+            float own_x = 0.f, own_y = 0.f, own_w = 0.f;  // p2f partial sums: lane j owns chunk face j
+
+            int ja = cbeg;
+            while (ja < cend) {
+                const uint32_t kb0 = s_boff[ja];
+                int jb = ja + 1;
+                while (jb < cend && s_boff[jb + 1] - kb0 <= (uint32_t)SUB_BLOCKS) ++jb;
+                const uint32_t kb1 = s_boff[jb];
+
+                // ---------------- phase A: pair-parallel geometry ----------------
+                {
+                    int j = ja;
+                    for (uint32_t k = kb0 + warp; k < kb1; k += NWARP) {
+                        while (s_boff[j + 1] <= k) ++j;  // warp-uniform, monotone
+                        const uint32_t geo = s_geo[j];
+                        const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
+                        const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
+                        const int local = (int)(k - s_boff[j]) * 32 + lane;
+                        const int slot = (int)(k - kb0) * 32 + lane;
+                        const float* rc = chunk + (j - cbeg) * REC_F;
+                        uint32_t tflags = 0;
+                        bool emit = false;
+                        Frag fr;
+                        float k0 = 0.f, k1 = 0.f, k2 = 0.f, zp = 0.f;
+                        int pix = 0;
+                        if (local < w * h) {
+                            const uint32_t rcpw = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // exact floor(l / w): l < 1024, w <= 32
+                            const int lr = (int)(((uint32_t)local * rcpw) >> 16);
+                            const int col = cx0 + (local - lr * w), row = ry0 + lr;
+                            pix = row * TILE + col;
+                            if (fragment(rc, s_xp[col], s_yp[row], K.thr, K.sigma, fr)) {
+                                k0 = fr.w0; k1 = fr.w1; k2 = fr.w2;
+                                clip_bary(k0, k1, k2);
+                                zp = depth_of(rc, k0, k1, k2);
+                                const bool zv = !(zp < K.near_ || zp > K.far_);
+                                const uint32_t flg = __float_as_uint(rc[R_FLG]);
+                                tflags = SL_VALID | (zv ? SL_ZV : 0u) | ((flg & 8u) ? SL_FRONT : 0u) |
+                                         (uint32_t)texel_index(k0, k1, K.R);
+                                if (RGB == 0) {
+                                    const bool inside = fr.w0 <= 1 && fr.w0 >= 0 && fr.w1 <= 1 && fr.w1 >= 0 &&
+                                                        fr.w2 <= 1 && fr.w2 >= 0;
+                                    if (inside) tflags |= SL_INS;
+                                    s_sZ[slot] = zp;
+                                } else {
+                                    s_sZ[slot] = (K.far_ - zp) / (K.far_ - K.near_);  // kernel.cu:418
+                                }
+                                s_sD[slot] = fr.D;
+                                emit = zv;  // kernel.cu:592 drops every gradient of an out-of-range pair
+                            }
+                            s_sT[slot] = tflags;
+                        }
+                        if (save) {  // uniform
+                            const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                            if (emit) {
+                                const int pos = __popc(m & lt);
+                                float4* dst = pb.recs + (size_t)(segbase + k) * BLK_F4 + pos;
+                                // closest-point barycentrics as the reference forms them: t_k + w_k (kernel.cu:638-641)
+                                const float u0 = fr.t0 + fr.w0, u1 = fr.t1 + fr.w1, u2 = fr.t2 + fr.w2;
+                                const uint32_t meta = (uint32_t)pix | ((tflags & SL_TIX) << 8) | ((tflags & SL_FRONT) ? (1u << 24) : 0u);
+                                dst[0] = make_float4(fr.D, fr.sign * fr.dx, fr.sign * fr.dy, zp);
+                                dst[32] = make_float4(u0, u1, u2, __uint_as_float(meta));
+                                dst[64] = make_float4(k0 / rc[2] / rc[2], k1 / rc[5] / rc[5], k2 / rc[8] / rc[8], 0.f);
+                            }
+                            if (lane == 0) pb.blk_hdr[segbase + k] = (uint32_t)s_list[j] | ((uint32_t)__popc(m) << 16);
+                        }
+                    }
+                }
+                __syncthreads();
+
+                // ---------------- phase B: ordered per-pixel aggregation ----------------
+                {
+                    // faces of the sub-chunk whose rectangle meets this warp's 8x4 block (lane i <-> face ja + i)
+                    bool meets = false;
+                    if (ja + lane < jb) {
+                        const uint32_t g = s_geo[ja + lane];
+                        const int cx0 = (int)(g & 15u), w = (int)((g >> 4) & 31u);
+                        const int ry0 = (int)((g >> 9) & 15u), h = (int)((g >> 13) & 31u);
+                        meets = w > 0 && h > 0 && cx0 < bx0 + 8 && cx0 + w > bx0 && ry0 < by0 + 4 && ry0 + h > by0;
+                    }
+                    uint32_t fm = __ballot_sync(0xffffffffu, meets);
+                    while (fm) {
+                        const int i = __ffs(fm) - 1;
+                        fm &= fm - 1u;
+                        const int j = ja + i;
+                        const uint32_t geo = s_geo[j];
+                        const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
+                        const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
+                        const int dc = lcol - cx0, dr = lrow - ry0;
+                        float a_x = 0.f, a_y = 0.f, a_w = 0.f;
+                        bool contrib = false;
+                        if (live && (unsigned)dc < (unsigned)w && (unsigned)dr < (unsigned)h) {
+                            const int slot = (int)(s_boff[j] - kb0) * 32 + dr * w + dc;
+                            const uint32_t t = s_sT[slot];
+                            if (t & SL_VALID) {
+                                const float D = s_sD[slot];
+                                acc_a = (float)((double)acc_a * (1. - (double)D));  // kernel.cu:396
+                                if (t & SL_ZV) {
+                                    const int f = s_list[j];
+                                    const bool front = (t & SL_FRONT) != 0;
+                                    if (RGB == 0) {
+                                        const float zp = s_sZ[slot];
+                                        if (zp < zmin && (t & SL_INS) && (K.double_side || front)) {
+                                            zmin = zp;
+                                            fid = f;
+                                            const float* tp = tex_img + ((size_t)f * K.T2 + (t & SL_TIX)) * 3;
+                                            c0 = __ldg(tp); c1 = __ldg(tp + 1); c2 = __ldg(tp + 2);
+                                        }
+                                    } else if (front || K.double_side) {
+                                        const float zn = s_sZ[slot];
+                                        float ed = 1.f;
+                                        if (zn > smax) { ed = expf((smax - zn) / K.gamma); smax = zn; }
+                                        const float ez = expf((zn - smax) / K.gamma);
+                                        ssum = ed * ssum + ez * D;
+                                        const float a = ez * D;
+                                        if (a != 0.f || ed != 1.f) {  // else: c = 1*c + 0*texel, p2f terms 0 (exact)
+                                            a_x = a * gx; a_y = a * gy; a_w = a;
+                                            contrib = a != 0.f;
+                                            const float* tp = tex_img + ((size_t)f * K.T2 + (t & SL_TIX)) * 3;
+                                            c0 = ed * c0 + a * __ldg(tp);
+                                            c1 = ed * c1 + a * __ldg(tp + 1);
+                                            c2 = ed * c2 + a * __ldg(tp + 2);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        if (RGB == 1 && p2f_acc != nullptr) {
+                            if (__any_sync(0xffffffffu, contrib)) {
+                                a_x = warp_sum(a_x); a_y = warp_sum(a_y); a_w = warp_sum(a_w);
+                                if (lane == j - cbeg) { own_x += a_x; own_y += a_y; own_w += a_w; }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();  // slots free
+                ja = jb;
+            }
+            if (RGB == 1 && p2f_acc != nullptr && own_w != 0.f) {  // one global RED per (warp, face, component)
+                float* dst = p2f_acc + ((size_t)b * F + s_list[cbeg + lane]) * 4;
+                red_add_global(dst + 0, own_x);
+                red_add_global(dst + 1, own_y);
+                red_add_global(dst + 2, own_w);
+            }
+            issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);  // stage st is free (barrier above); commits an empty group past the end
+        }
+        cp_async_wait<0>();
+        __syncthreads();  // segment done: s_list / s_geo / s_boff / s_rec reusable
+    }
+    if (tid == 0 && pb.cap > 0) pb.tile_head[tile_id] = head;
+
+    // ---- finalise (kernel.cu:443-475) + fused 2x2 pool + coalesced stores (as round 1) --------------------
+    const float alpha = (float)(1. - (double)acc_a);  // kernel.cu:449-451
+    float o0, o1, o2, g0, g1;
+    if (RGB == 0) {
+        o0 = c0; o1 = c1; o2 = c2;
+        g0 = zmin; g1 = (float)fid;
+    } else {
+        o0 = c0 == 0.f ? c0 : c0 / ssum;
+        o1 = c1 == 0.f ? c1 : c1 / ssum;
+        o2 = c2 == 0.f ? c2 : c2 / ssum;
+        g0 = ssum; g1 = smax;
+    }
+    const size_t np = (size_t)S * S;
+    float v[4] = {o0, o1, o2, alpha};
+    if (K.aa) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a01 = __shfl_xor_sync(0xffffffffu, v[k], 1);
+            const float a10 = __shfl_xor_sync(0xffffffffu, v[k], 8);
+            const float a11 = __shfl_xor_sync(0xffffffffu, v[k], 9);
+            v[k] = (((v[k] + a01) + a10) + a11) * 0.25f;  // meaningful on the (even x, even y) lane
+        }
+    }
+    if (K.aa && K.vec_store && tx0 + TILE <= S && ty0 + TILE <= S) {  // uniform: full tile, aligned buffers
+        float* st = s_rec;  // 6 * 256 + 4 * 64 = 1792 floats <= 2048
+        const int o = lrow * TILE + lcol;
+        st[0 * 256 + o] = o0; st[1 * 256 + o] = o1; st[2 * 256 + o] = o2; st[3 * 256 + o] = alpha;
+        st[4 * 256 + o] = g0; st[5 * 256 + o] = g1;
+        if ((lane & 1) == 0 && (lane & 8) == 0) {
+            const int po = (lrow >> 1) * (TILE / 2) + (lcol >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st[6 * 256 + k * 64 + po] = v[k];
+        }
+        __syncthreads();
+        for (int i = tid; i < 6 * 64; i += CTA) {
+            const int plane = i >> 6, rem = i & 63, row = rem >> 2, q = rem & 3;
+            const float4 val = *reinterpret_cast<const float4*>(st + plane * 256 + row * TILE + q * 4);
+            const size_t off = (size_t)(ty0 + row) * S + tx0 + q * 4;
+            if (plane < 4) {
+                if (colors_hi != nullptr)
+                    *reinterpret_cast<float4*>(colors_hi + ((size_t)b * 4 + plane) * np + off) = val;
+            } else {
+                *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - 4)) * np + off) = val;
+            }
+        }
+        if (tid < 64) {
+            const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
+            const float4 val = *reinterpret_cast<const float4*>(st + 6 * 256 + k * 64 + row * (TILE / 2) + q * 4);
+            const int IS = K.IS;
+            const size_t nq = (size_t)IS * IS;
+            *reinterpret_cast<float4*>(images + ((size_t)b * 4 + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) = val;
+        }
+        return;
+    }
+    if (live) {
+        const size_t p = (size_t)py * S + px;
+        aggrs[((size_t)b * 2 + 0) * np + p] = g0;
+        aggrs[((size_t)b * 2 + 1) * np + p] = g1;
+        if (colors_hi != nullptr) {
+            colors_hi[((size_t)b * 4 + 0) * np + p] = o0;
+            colors_hi[((size_t)b * 4 + 1) * np + p] = o1;
+            colors_hi[((size_t)b * 4 + 2) * np + p] = o2;
+            colors_hi[((size_t)b * 4 + 3) * np + p] = alpha;
+        }
+    }
+    if (K.aa) {
+        if (live && (lane & 1) == 0 && (lane & 8) == 0) {
+            const int IS = K.IS;
+            const size_t q = (size_t)(py >> 1) * IS + (px >> 1);
+            const size_t nq = (size_t)IS * IS;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * nq + q] = v[k];
+        }
+    } else if (live && images != colors_hi) {
+        const size_t p = (size_t)py * S + px;
+        images[((size_t)b * 4 + 0) * np + p] = o0;
+        images[((size_t)b * 4 + 1) * np + p] = o1;
+        images[((size_t)b * 4 + 2) * np + p] = o2;
+        images[((size_t)b * 4 + 3) * np + p] = alpha;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: stream the saved pair records of the tile
+// ---------------------------------------------------------------------------------------------
+template <int RGB, bool TEXGRAD>
+__global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
+                                                        const float* __restrict__ aggrs, const float* __restrict__ grad_images,
+                                                        float* __restrict__ grad_faces, float* __restrict__ grad_tex, Consts K,
+                                                        PairBuf pb) {
+    __shared__ float s_pix[10][TILE * TILE];  // g0..g3, C0..C3, ssum, smax (row-major tile pixels)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int S = K.S, F = K.F;
+    const size_t tile_id = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int32_t head = __ldg(pb.tile_head + tile_id);
+    if (head < 0) return;  // empty, or unsaved (k_raster_bwd_pairs handles it)
+    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
+    {
+        const int px = x0 + (tid % TILE), py = y0 + (tid / TILE);
+        const size_t np = (size_t)S * S;
+        float v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+        if (px < S && py < S) {
+            const size_t p = (size_t)py * S + px;
+            if (K.aa) {  // avg_pool2d backward: g / 4
+                const size_t nq = (size_t)K.IS * K.IS;
+                const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * nq + q) * 0.25f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * np + p);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[4 + k] = __ldg(colors_hi + ((size_t)b * 4 + k) * np + p);
+            v[8] = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
+            v[9] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s_pix[k][tid] = v[k];
+    }
+    __syncthreads();
+    const float* tex_img = textures + (size_t)b * F * K.T2 * 3;
+    float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * F * K.T2 * 3 : nullptr;
+    float* gf_img = grad_faces + (size_t)b * F * 9;
+
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    int cur_f = -1;
+    auto flush = [&]() {
+        if (cur_f >= 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
+            if (lane < 9) {
+                float v = acc[0];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) v = (lane == k) ? acc[k] : v;
+                if (v != 0.f) red_add_global(gf_img + (size_t)cur_f * 9 + lane, v);
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+        }
+    };
+
+    uint32_t seg = (uint32_t)head;
+    while (seg != SEG_NONE) {
+        const uint32_t NB = __ldg(pb.blk_hdr + seg), next = __ldg(pb.blk_hdr + seg + 1);
+        const uint32_t per = (NB + NWARP - 1) / NWARP;
+        const uint32_t kbeg = min(NB, warp * per), kend = min(NB, kbeg + per);
+        for (uint32_t k = kbeg; k < kend; ++k) {
+            const uint32_t hdr = __ldg(pb.blk_hdr + seg + 2 + k);
+            const int cnt = (int)(hdr >> 16);
+            if (cnt == 0) continue;  // warp-uniform
+            const int f = (int)(hdr & 0xffffu);
+            if (f != cur_f) { flush(); cur_f = f; }
+            if (lane < cnt) {
+                const float4* src = pb.recs + (size_t)(seg + 2 + k) * BLK_F4 + lane;
+                const float4 r0 = __ldg(src), r1 = __ldg(src + 32), r2 = __ldg(src + 64);
+                const float D = r0.x, sdx = r0.y, sdy = r0.z, zp = r0.w;
+                const uint32_t meta = __float_as_uint(r1.w);
+                const int pix = (int)(meta & 0xffu), tix = (int)((meta >> 8) & 0xffffu);
+                const bool front = (meta >> 24) & 1u;
+                const float* sp = &s_pix[0][pix];
+                const float g3 = sp[3 * 256];
+                const float one_m_a = 1 - sp[7 * 256];
+                // g3 * ((1 - alpha) / max(1 - D, 1e-6)) (kernel.cu:584); zero cases answered directly
+                float Cxy = (one_m_a == 0.f || g3 == 0.f)
+                                ? g3 * one_m_a
+                                : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - D), 1e-6)));
+                if (RGB == 0) {
+                    if ((float)f == sp[9 * 256]) {  // aggrs[1] = winning face id (:596)
+                        if (TEXGRAD) {
+                            float* gt = gtex_img + ((size_t)f * K.T2 + tix) * 3;
+                            red_add_global(gt + 0, sp[0]);
+                            red_add_global(gt + 1, sp[1 * 256]);
+                            red_add_global(gt + 2, sp[2 * 256]);
+                        }
+                    }
+                } else if (front || K.double_side) {
+                    const float g0 = sp[0], g1 = sp[1 * 256], g2 = sp[2 * 256];
+                    if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
+                        const float zn = (K.far_ - zp) / (K.far_ - K.near_);
+                        const float s = D * expf((zn - sp[9 * 256]) / K.gamma) / sp[8 * 256];  // :608
+                        if (s != 0.f) {
+                            const size_t to = ((size_t)f * K.T2 + tix) * 3;
+                            if (TEXGRAD) {
+                                red_add_global(gtex_img + to + 0, s * g0);
+                                red_add_global(gtex_img + to + 1, s * g1);
+                                red_add_global(gtex_img + to + 2, s * g2);
+                            }
+                            float Crgb = 0.f;
+                            Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * 256]);
+                            Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * 256]);
+                            Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * 256]);
+                            Crgb *= s;
+                            if (Crgb != 0.f) {
+                                Cxy += Crgb / D;
+                                const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
+                                acc[2] += Cz * r2.x;
+                                acc[5] += Cz * r2.y;
+                                acc[8] += Cz * r2.z;
+                            }
+                        }
+                    }
+                }
+                Cxy *= D * (1 - D) / K.sigma;  // :632
+                const float q = 2 * Cxy;       // :640 (the sign rides in sdx / sdy)
+                acc[0] += q * r1.x * sdx;
+                acc[1] += q * r1.x * sdy;
+                acc[3] += q * r1.y * sdx;
+                acc[4] += q * r1.y * sdy;
+                acc[6] += q * r1.z * sdx;
+                acc[7] += q * r1.z * sdy;
+            }
+        }
+        seg = next;
+    }
+    flush();
+}
+
+}  // namespace umr

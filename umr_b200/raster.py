@@ -11,6 +11,7 @@ There is NO CPU path: CPU tensors raise (the reference intends the same, soft_ra
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -84,6 +85,23 @@ def collect_profile(sink):
     return out
 
 
+# --- pair buffer (saved (pixel, face) records streamed by the backward; include/umr_b200.h) -------------
+# Budget in candidate pairs per raster pixel (measured: 2.7 at F=1280, 4.8 at F=5120) and an
+# upper bound on one render's buffer; tiles that do not fit are recomputed by the backward (same results).
+PAIR_CAND_PER_PIXEL = float(os.environ.get("UMR_PAIR_CAND_PER_PIXEL", "6.0"))
+PAIR_MAX_BYTES = int(float(os.environ.get("UMR_PAIR_MAX_GB", "24")) * (1 << 30))
+
+
+def pair_buffer_bytes(B, image_size, anti_aliasing, cand_per_pixel=None):
+    lib = _lib.load()
+    S = int(image_size) * (2 if anti_aliasing else 1)
+    cpp = PAIR_CAND_PER_PIXEL if cand_per_pixel is None else cand_per_pixel
+    tiles = B * ((S + 15) // 16) ** 2
+    blocks = int(B * S * S * cpp / 32.0) + 2 * tiles + 64
+    nbytes = lib.umr_raster_pair_buffer_bytes(B, int(image_size), 1 if anti_aliasing else 0, blocks)
+    return min(int(nbytes), PAIR_MAX_BYTES)
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -141,7 +159,13 @@ class SoftRasterizeFunction(torch.autograd.Function):
                 colors_hi = images
             aggrs = torch.empty(B, 2, S, S, device=dev, dtype=torch.float32)
             p2f = torch.empty(B, F, 2, device=dev, dtype=torch.float32)
-            ws = torch.empty(lib.umr_raster_workspace_bytes(B, F), device=dev, dtype=torch.uint8)
+            ws = torch.empty(lib.umr_raster_workspace_bytes(B, F, int(image_size), params.anti_aliasing), device=dev,
+                             dtype=torch.uint8)
+            pairs = None
+            generic = dist_func != "euclidean" or aggr_func_alpha != "prod" or texture_type != "surface"
+            if need_bwd and not generic and PAIR_CAND_PER_PIXEL > 0:
+                pairs = torch.empty(pair_buffer_bytes(B, image_size, anti_aliasing), device=dev, dtype=torch.uint8)
+                params.pair_buffer, params.pair_buffer_bytes = pairs.data_ptr(), pairs.numel()
             rc = lib.umr_raster_forward(_ptr(fv), _ptr(tex), _ptr(images),
                                         _ptr(colors_hi) if anti_aliasing else _ptr(None),
                                         _ptr(aggrs), _ptr(p2f), ctypes.byref(params), _ptr(ws),
@@ -151,15 +175,23 @@ class SoftRasterizeFunction(torch.autograd.Function):
         ctx.params = params
         ctx.in_shape = tuple(face_vertices.shape)
         ctx.tex_needs_grad = textures.requires_grad
+        ctx.has_pairs = pairs is not None
         if need_bwd:
-            ctx.save_for_backward(fv, tex, colors_hi, aggrs)
+            if pairs is not None:
+                ctx.save_for_backward(fv, tex, colors_hi, aggrs, pairs)
+            else:
+                ctx.save_for_backward(fv, tex, colors_hi, aggrs)
         ctx.mark_non_differentiable(p2f, aggrs)
         return images, p2f, aggrs
 
     @staticmethod
     def backward(ctx, grad_images, grad_p2f=None, grad_aggrs=None):
         lib = _lib.load()
-        fv, tex, colors_hi, aggrs = ctx.saved_tensors
+        if ctx.has_pairs:
+            fv, tex, colors_hi, aggrs, pairs = ctx.saved_tensors
+            assert ctx.params.pair_buffer == pairs.data_ptr()
+        else:
+            fv, tex, colors_hi, aggrs = ctx.saved_tensors
         dev = fv.device
         B, F = fv.shape[:2]
         g = grad_images.contiguous().float()
@@ -167,7 +199,8 @@ class SoftRasterizeFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             grad_faces = torch.empty_like(fv)
             grad_tex = torch.empty_like(tex) if ctx.tex_needs_grad else None
-            ws = torch.empty(lib.umr_raster_workspace_bytes(B, F), device=dev, dtype=torch.uint8)
+            ws = torch.empty(lib.umr_raster_workspace_bytes(B, F, ctx.params.image_size, ctx.params.anti_aliasing),
+                             device=dev, dtype=torch.uint8)
             rc = lib.umr_raster_backward(_ptr(fv), _ptr(tex), _ptr(colors_hi), _ptr(aggrs), _ptr(g),
                                          _ptr(grad_faces), _ptr(grad_tex), ctypes.byref(ctx.params),
                                          _ptr(ws), _stream_ptr(dev))
