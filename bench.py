@@ -139,7 +139,10 @@ def cpu_arm(cfg, steps, warmup, budget_s=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import softras
     impl, kind = ("A", "reference") if softras.have_oracle_a() else ("B", "port")
-    cores = os.cpu_count() or 1
+    # threads actually usable by this process (affinity mask and cgroup quota), not os.cpu_count(): on a shared box
+    # the latter oversubscribes OpenMP and made the round-1 CPU arm swing 5.7x between boxes
+    cores = softras.host_threads(cap=256)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
     sub = 2  # bounded sample: a 2-image sub-batch of the workload per step
     fv, tex, g = cpu_workload(cfg, sub)
     for _ in range(max(warmup, 1)):
@@ -153,9 +156,9 @@ def cpu_arm(cfg, steps, warmup, budget_s=None):
             break
     dt = time.perf_counter() - t0
     ips = done * sub / dt
-    info = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+    info = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "host_cpu_count": os.cpu_count(),
             "sample": "%d step(s) x %d-image sub-batch of %s, rasteriser core fwd+bwd (prep+forward+2x2 pool+"
-                      "backward), OpenMP over all host threads" % (done, sub, cfg["name"])}
+                      "backward), OpenMP over the threads this process may use (affinity + cgroup quota)" % (done, sub, cfg["name"])}
     return ips, dt / done * 1e3, info
 
 

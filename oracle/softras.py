@@ -53,8 +53,34 @@ def have_oracle_a():
         return False
 
 
+def host_threads(cap=64):
+    """Threads the oracle may use: the CPUs this process can actually run on -- the scheduler affinity mask, further
+    limited by a cgroup CPU quota (cpu.max / cfs_quota) -- NOT os.cpu_count(), which on a shared GPU box reports
+    every core of the machine and oversubscribes OpenMP (round-1 VERDICT: 3.4 vs 20 images/s on "128 cores")."""
+    import math
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:  # cgroup v2: "<quota> <period>" or "max <period>"
+            q, per = fh.read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, int(math.ceil(int(q) / float(per)))))
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fq, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fp:
+                q, per = int(fq.read()), int(fp.read())
+                if q > 0:
+                    n = min(n, max(1, int(math.ceil(q / float(per)))))
+        except Exception:
+            pass
+    return max(1, min(n, cap))
+
+
 def max_threads():
-    return _lib("B").oracle_max_threads()
+    return host_threads()
+
+
+def _nt(nthreads):
+    return host_threads() if nthreads <= 0 else nthreads
 
 
 def _p(a):
@@ -113,7 +139,7 @@ def forward(face_vertices, textures, cfg, impl="B", nthreads=0, dtype=np.float32
     sfx = "f32" if dtype == np.float32 else "f64"
     fn = getattr(lib, ("ref_" if impl == "A" else "oracle_") + "forward_soft_rasterize_" + sfx)
     fn(_p(fv), _p(tex), _p(faces_info), _p(aggrs), _p(grid), _p(p2f), _p(p2f_sum), _p(colors),
-       B, F, S, T2, *cfg.scalars(), ctypes.c_int(nthreads))
+       B, F, S, T2, *cfg.scalars(), ctypes.c_int(_nt(nthreads)))
     p2f_info = p2f / np.maximum(p2f_sum, dtype(1e-12))  # soft_rasterize.py:73
     return dict(soft_colors=colors, p2f_info=p2f_info, aggrs_info=aggrs, faces_info=faces_info,
                 p2f_raw=p2f, p2f_sum=p2f_sum, face_vertices=fv, textures=tex)
@@ -136,12 +162,12 @@ def backward(fwd, grad_soft_colors, cfg, impl="B", ub_texgrad=False, nthreads=0)
     if impl == "A":
         fn = getattr(lib, "ref_backward_soft_rasterize_" + sfx)
         fn(_p(fv), _p(tex), _p(fwd["soft_colors"]), _p(fwd["faces_info"]), _p(fwd["aggrs_info"]),
-           _p(gf), _p(gt), _p(g), B, F, S, T2, *cfg.scalars(), ctypes.c_int(nthreads))
+           _p(gf), _p(gt), _p(g), B, F, S, T2, *cfg.scalars(), ctypes.c_int(_nt(nthreads)))
     else:
         fn = getattr(lib, "oracle_backward_soft_rasterize_" + sfx)
         fn(_p(fv), _p(tex), _p(fwd["soft_colors"]), _p(fwd["faces_info"]), _p(fwd["aggrs_info"]),
            _p(gf), _p(gt), _p(g), B, F, S, T2, *cfg.scalars(), ctypes.c_int(1 if ub_texgrad else 0),
-           ctypes.c_int(nthreads))
+           ctypes.c_int(_nt(nthreads)))
     return gf, gt
 
 

@@ -39,6 +39,13 @@ def main():
         torch.cuda.synchronize()
         tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
     tf /= a.iters; tb /= a.iters
+    img, _, _ = raster.soft_rasterize(fv, tex, a.isz, **kw)
+    sv = img.grad_fn.saved_tensors
+    if len(sv) == 5:
+        st = sv[4][:8].view(torch.int32).cpu().tolist()
+        S = 2 * a.isz
+        print("pair buffer: %.1f MB, blocks wanted %d (%.2f candidates-slots/pixel), tiles unsaved %d" % (
+            sv[4].numel() / 1e6, st[0], st[0] * 32.0 / (a.B * S * S), st[1]))
     print("B=%d is=%d F=%d T2=%d %s: fwd %.3f ms  bwd %.3f ms  -> %.0f img/s (fwd+bwd), alpha mean %.4f" % (
         a.B, a.isz, f.shape[0], a.R * a.R, a.rgb, tf, tb, a.B / ((tf + tb) * 1e-3), img[:, 3].mean().item()))
 

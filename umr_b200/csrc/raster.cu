@@ -54,7 +54,7 @@ constexpr int R_INV = 9;   // 9 : barycentric inverse, row-major
 constexpr int R_SYM = 18;  // 6 : s00 s01 s02 s11 s12 s22   (Gram + 1)
 constexpr int R_BOX = 24;  // 4 : xlo xhi ylo yhi (cull box, already expanded by r)
 constexpr int R_FLG = 28;  // 1 : bit0..2 obtuse corner, bit3 front-facing
-// 29..31 pad
+constexpr int R_IZ2 = 29;  // 3 : 1 / (z_k * z_k)  (backward z-gradient factor, saved per pair by the forward)
 
 struct WorkspaceLayout {
     size_t rec_off, box_off, p2f_off, ubox_off, ccount_off, clist_off, total;
@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ fv, floa
     else if ((x0 - x2) * (x1 - x2) + (y0 - y2) * (y1 - y2) < 0) flags = 4;
     if ((y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0)) flags |= 8;  // kernel.cu:42-44
     out[R_FLG] = __uint_as_float(flags);
-    out[29] = out[30] = out[31] = 0.f;
+    out[R_IZ2 + 0] = 1.f / (v[2] * v[2]);
+    out[R_IZ2 + 1] = 1.f / (v[5] * v[5]);
+    out[R_IZ2 + 2] = 1.f / (v[8] * v[8]);
     if (valid) {
         float4* dst = reinterpret_cast<float4*>(rec + (size_t)i * REC_F);
 #pragma unroll
@@ -312,6 +314,7 @@ __device__ __forceinline__ int texel_index(float c0, float c1, int R) {  // kern
 
 struct Consts {
     float thr, sigma, gamma, near_, far_, inv_unused;
+    float r_sigma, r_gamma, r_fn, r_nf;  // 1/sigma, 1/gamma, 1/(far-near), 1/(near-far): streamed backward only
     int F, T2, R, S, IS, aa, double_side;
     int dist, alpha, tex;  // mode ids (read only by the GEN=true instantiations)
     int vec_store;         // 1: forward may use the shared-staged 128-bit store epilogue (alignment checked on host)
@@ -1357,6 +1360,10 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.near_ = p->near_plane;
     K.far_ = p->far_plane;
     K.inv_unused = 0.f;
+    K.r_sigma = (float)(1.0 / (double)p->sigma_val);
+    K.r_gamma = (float)(1.0 / (double)p->gamma_val);
+    K.r_fn = (float)(1.0 / ((double)p->far_plane - (double)p->near_plane));
+    K.r_nf = (float)(1.0 / ((double)p->near_plane - (double)p->far_plane));
     K.F = p->num_faces;
     K.T2 = p->texture_size;
     K.R = (int)sqrt((double)p->texture_size);  // kernel.cu:685
@@ -1390,6 +1397,7 @@ static int ensure_smem_attrs() {
                              optin - (int)fa.sharedSizeBytes);                                       \
     if (e != cudaSuccess) return (int)e;
     UMR_SET((k_raster_fwd<0, true>)) UMR_SET((k_raster_fwd<1, true>))
+    UMR_SET((k_raster_fwd2<0>)) UMR_SET((k_raster_fwd2<1>))
     UMR_SET((k_raster_bwd<0, false, false>)) UMR_SET((k_raster_bwd<0, true, false>))
     UMR_SET((k_raster_bwd<1, false, false>)) UMR_SET((k_raster_bwd<1, true, false>))
     UMR_SET((k_raster_bwd<0, false, true>)) UMR_SET((k_raster_bwd<0, true, true>))
@@ -1451,15 +1459,16 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
             cudaError_t e = cudaMemsetAsync(pb.ctrl, 0, 16, stream);
             if (e != cudaSuccess) return (int)e;
         }
+        const size_t fwd2_smem = (size_t)2 * SLOTS * 12;  // two slot buffers (D, depth, flags)
         count_launch(2);
         k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
         if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
         if (softmax)
-            k_raster_fwd2<1><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc,
+            k_raster_fwd2<1><<<grid, CTA, fwd2_smem, stream>>>(rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc,
                                                        ubox, K, p->eps, p->background_color[0], p->background_color[1],
                                                        p->background_color[2], pb, ncb);
         else
-            k_raster_fwd2<0><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc,
+            k_raster_fwd2<0><<<grid, CTA, fwd2_smem, stream>>>(rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc,
                                                        ubox, K, p->eps, p->background_color[0], p->background_color[1],
                                                        p->background_color[2], pb, ncb);
         if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);

@@ -105,9 +105,12 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
                                                         float* __restrict__ p2f_acc, const uint32_t* __restrict__ ubox,
                                                         Consts K, float eps, float bg0, float bg1, float bg2, PairBuf pb,
                                                         int ncb) {
+    // dynamic shared memory: two slot buffers (phase A of sub-chunk i+1 overlaps phase B of sub-chunk i)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_sD = reinterpret_cast<float*>(smem_raw);                       // [2][SLOTS]
+    float* s_sZ = s_sD + 2 * SLOTS;                                         // [2][SLOTS]
+    uint32_t* s_sT = reinterpret_cast<uint32_t*>(s_sZ + 2 * SLOTS);         // [2][SLOTS]
     __shared__ __align__(128) float s_rec[NSTAGE * CHUNK * REC_F];  // 8 KB; reused by the store epilogue
-    __shared__ float s_sD[SLOTS], s_sZ[SLOTS];
-    __shared__ uint32_t s_sT[SLOTS];
     __shared__ uint16_t s_list[LCAP];
     __shared__ uint32_t s_geo[LCAP];
     __shared__ uint32_t s_boff[LCAP + 1];
@@ -120,13 +123,8 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int S = K.S, F = K.F;
-    const PixelMap pm = map_pixel(S);
-    const int px = pm.px, py = pm.py;
-    const bool live = pm.live;
     const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
-    const int lcol = px - tx0, lrow = py - ty0;       // pixel position inside the tile
-    const int ncol = min(TILE, S - tx0), nrow = min(TILE, S - ty0);
-    const int bx0 = (warp & 1) * 8, by0 = (warp >> 1) * 4;  // this warp's 8x4 pixel block inside the tile
+    const size_t np = (size_t)S * S;
 
     tile_extents(S, s_ext);
     if (tid < TILE) s_xp[tid] = pixel_coord(tx0 + tid, S);
@@ -137,6 +135,85 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
     const size_t tile_id = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const size_t cidx = ((size_t)b * ncb + (ty0 / CB)) * ncb + (tx0 / CB);
     const int nc = tile_outside_union(ubox, b, s_ext) ? 0 : __ldg(ccount + cidx);
+
+    if (nc == 0) {
+        // ---- untouched tile (most of the image): every pixel holds the initial state.  Same arithmetic as the
+        // general path (kernel.cu:335-348, 443-475), evaluated once, stored with 128-bit stores where possible.
+        if (tid == 0 && pb.cap > 0) pb.tile_head[tile_id] = TILE_EMPTY;
+        const float ssum0 = expf(eps / K.gamma);
+        float o0, o1, o2, g0, g1;
+        if (RGB == 0) {
+            o0 = bg0; o1 = bg1; o2 = bg2;
+            g0 = 10000000.f; g1 = -1.f;
+        } else {
+            const float q0 = bg0 * ssum0, q1 = bg1 * ssum0, q2 = bg2 * ssum0;
+            o0 = q0 == 0.f ? q0 : q0 / ssum0;
+            o1 = q1 == 0.f ? q1 : q1 / ssum0;
+            o2 = q2 == 0.f ? q2 : q2 / ssum0;
+            g0 = ssum0; g1 = eps;
+        }
+        const float alpha = (float)(1. - (double)1.f);
+        const float full[6] = {o0, o1, o2, alpha, g0, g1};
+        float pooled[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pooled[k] = (((full[k] + full[k]) + full[k]) + full[k]) * 0.25f;
+        if (K.aa && K.vec_store && tx0 + TILE <= S && ty0 + TILE <= S) {
+            for (int i = tid; i < 6 * 64; i += CTA) {
+                const int plane = i >> 6, rem = i & 63, row = rem >> 2, q = rem & 3;
+                float x = full[0];
+#pragma unroll
+                for (int k = 1; k < 6; ++k) x = (plane == k) ? full[k] : x;
+                const float4 val = make_float4(x, x, x, x);
+                const size_t off = (size_t)(ty0 + row) * S + tx0 + q * 4;
+                if (plane < 4) {
+                    if (colors_hi != nullptr)
+                        *reinterpret_cast<float4*>(colors_hi + ((size_t)b * 4 + plane) * np + off) = val;
+                } else {
+                    *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - 4)) * np + off) = val;
+                }
+            }
+            if (tid < 64) {
+                const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
+                float x = pooled[0];
+#pragma unroll
+                for (int kk = 1; kk < 4; ++kk) x = (k == kk) ? pooled[kk] : x;
+                const int IS = K.IS;
+                const size_t nq = (size_t)IS * IS;
+                *reinterpret_cast<float4*>(images + ((size_t)b * 4 + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) =
+                    make_float4(x, x, x, x);
+            }
+            return;
+        }
+        const int px = tx0 + (tid & (TILE - 1)), py = ty0 + (tid >> 4);
+        if (px < S && py < S) {
+            const size_t p = (size_t)py * S + px;
+            aggrs[((size_t)b * 2 + 0) * np + p] = g0;
+            aggrs[((size_t)b * 2 + 1) * np + p] = g1;
+            if (colors_hi != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) colors_hi[((size_t)b * 4 + k) * np + p] = full[k];
+            }
+            if (K.aa) {
+                if ((px & 1) == 0 && (py & 1) == 0 && px + 1 < S && py + 1 < S) {
+                    const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
+                    const size_t nq = (size_t)K.IS * K.IS;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * nq + q] = pooled[k];
+                }
+            } else if (images != colors_hi) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * np + p] = full[k];
+            }
+        }
+        return;
+    }
+
+    const PixelMap pm = map_pixel(S);
+    const int px = pm.px, py = pm.py;
+    const bool live = pm.live;
+    const int lcol = px - tx0, lrow = py - ty0;       // pixel position inside the tile
+    const int ncol = min(TILE, S - tx0), nrow = min(TILE, S - ty0);
+    const int bx0 = (warp & 1) * 8, by0 = (warp >> 1) * 4;  // this warp's 8x4 pixel block inside the tile
     const uint16_t* cl = clist + cidx * F;
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
@@ -248,9 +325,10 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
         }
         __syncthreads();
         const uint32_t NBw = s_boff[n];
+        if (NBw == 0) continue;  // uniform: every rectangle is empty
 
         // ---- reserve the segment's blocks in the pair buffer --------------------------------------------------
-        if (tid == 0 && s_save && NBw > 0) {
+        if (tid == 0 && s_save) {
             const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
             if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
                 s_save = 0;  // does not fit: the whole tile falls back to the recompute backward
@@ -265,166 +343,192 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
                 s_segbase = base + 2u;
             }
         }
-        // (made visible by the barrier inside the chunk loop before phase A)
 
         const int nchunk = (n + CHUNK - 1) / CHUNK;
         issue_chunk(rec_img, s_list, n, 0, s_rec);
         issue_chunk(rec_img, s_list, n, 1, s_rec);
-        for (int c = 0; c < nchunk; ++c) {
-            const int st = c % NSTAGE;
-            const int cbeg = c * CHUNK, cend = min(n, cbeg + CHUNK);
-            cp_async_wait<1>();
-            __syncthreads();  // chunk c landed for every thread; s_save / s_segbase visible
-            const float* chunk = s_rec + (size_t)st * CHUNK * REC_F;
-            const bool save = s_save != 0;
-            const uint32_t segbase = s_segbase;
-            float own_x = 0.f, own_y = 0.f, own_w = 0.f;  // p2f partial sums: lane j owns chunk face j
+        cp_async_wait<1>();
+        __syncthreads();  // chunk 0 landed for every thread; s_save / s_segbase visible
+        const bool save = s_save != 0;
+        const uint32_t segbase = s_segbase;
 
-            int ja = cbeg;
-            while (ja < cend) {
-                const uint32_t kb0 = s_boff[ja];
-                int jb = ja + 1;
-                while (jb < cend && s_boff[jb + 1] - kb0 <= (uint32_t)SUB_BLOCKS) ++jb;
-                const uint32_t kb1 = s_boff[jb];
-
-                // ---------------- phase A: pair-parallel geometry ----------------
-                {
-                    int j = ja;
-                    for (uint32_t k = kb0 + warp; k < kb1; k += NWARP) {
-                        while (s_boff[j + 1] <= k) ++j;  // warp-uniform, monotone
-                        const uint32_t geo = s_geo[j];
-                        const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
-                        const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
-                        const int local = (int)(k - s_boff[j]) * 32 + lane;
-                        const int slot = (int)(k - kb0) * 32 + lane;
-                        const float* rc = chunk + (j - cbeg) * REC_F;
-                        uint32_t tflags = 0;
-                        bool emit = false;
-                        Frag fr;
-                        float k0 = 0.f, k1 = 0.f, k2 = 0.f, zp = 0.f;
-                        int pix = 0;
-                        if (local < w * h) {
-                            const uint32_t rcpw = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // exact floor(l / w): l < 1024, w <= 32
-                            const int lr = (int)(((uint32_t)local * rcpw) >> 16);
-                            const int col = cx0 + (local - lr * w), row = ry0 + lr;
-                            pix = row * TILE + col;
-                            if (fragment(rc, s_xp[col], s_yp[row], K.thr, K.sigma, fr)) {
-                                k0 = fr.w0; k1 = fr.w1; k2 = fr.w2;
-                                clip_bary(k0, k1, k2);
-                                zp = depth_of(rc, k0, k1, k2);
-                                const bool zv = !(zp < K.near_ || zp > K.far_);
-                                const uint32_t flg = __float_as_uint(rc[R_FLG]);
-                                tflags = SL_VALID | (zv ? SL_ZV : 0u) | ((flg & 8u) ? SL_FRONT : 0u) |
-                                         (uint32_t)texel_index(k0, k1, K.R);
-                                if (RGB == 0) {
-                                    const bool inside = fr.w0 <= 1 && fr.w0 >= 0 && fr.w1 <= 1 && fr.w1 >= 0 &&
-                                                        fr.w2 <= 1 && fr.w2 >= 0;
-                                    if (inside) tflags |= SL_INS;
-                                    s_sZ[slot] = zp;
-                                } else {
-                                    s_sZ[slot] = (K.far_ - zp) / (K.far_ - K.near_);  // kernel.cu:418
-                                }
-                                s_sD[slot] = fr.D;
-                                emit = zv;  // kernel.cu:592 drops every gradient of an out-of-range pair
-                            }
-                            s_sT[slot] = tflags;
+        // ---------------- phase A: pair-parallel geometry of faces [ja, jb) (blocks [kb0, kb1)) -> slot buffer `buf`
+        auto phase_a = [&](int c, int ja, uint32_t kb0, uint32_t kb1, int buf) {
+            const float* chunk = s_rec + (size_t)(c % NSTAGE) * CHUNK * REC_F;
+            const int cbeg = c * CHUNK;
+            float* sD = s_sD + buf * SLOTS;
+            float* sZ = s_sZ + buf * SLOTS;
+            uint32_t* sT = s_sT + buf * SLOTS;
+            int j = ja;
+            for (uint32_t k = kb0 + warp; k < kb1; k += NWARP) {
+                while (s_boff[j + 1] <= k) ++j;  // warp-uniform, monotone
+                const uint32_t geo = s_geo[j];
+                const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
+                const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
+                const int local = (int)(k - s_boff[j]) * 32 + lane;
+                const int slot = (int)(k - kb0) * 32 + lane;
+                const float* rc = chunk + (j - cbeg) * REC_F;
+                uint32_t tflags = 0;
+                bool emit = false;
+                Frag fr;
+                float k0 = 0.f, k1 = 0.f, k2 = 0.f, zp = 0.f;
+                int pix = 0;
+                if (local < w * h) {
+                    const uint32_t rcpw = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // exact floor(l / w): l < 1024, w <= 32
+                    const int lr = (int)(((uint32_t)local * rcpw) >> 16);
+                    const int col = cx0 + (local - lr * w), row = ry0 + lr;
+                    pix = row * TILE + col;
+                    if (fragment(rc, s_xp[col], s_yp[row], K.thr, K.sigma, fr)) {
+                        k0 = fr.w0; k1 = fr.w1; k2 = fr.w2;
+                        clip_bary(k0, k1, k2);
+                        zp = depth_of(rc, k0, k1, k2);
+                        const bool zv = !(zp < K.near_ || zp > K.far_);
+                        const uint32_t flg = __float_as_uint(rc[R_FLG]);
+                        tflags = SL_VALID | (zv ? SL_ZV : 0u) | ((flg & 8u) ? SL_FRONT : 0u) |
+                                 (uint32_t)texel_index(k0, k1, K.R);
+                        if (RGB == 0) {
+                            const bool inside = fr.w0 <= 1 && fr.w0 >= 0 && fr.w1 <= 1 && fr.w1 >= 0 &&
+                                                fr.w2 <= 1 && fr.w2 >= 0;
+                            if (inside) tflags |= SL_INS;
+                        } else {
+                            // normalised depth (kernel.cu:418).  The backward needs THESE bits: its softmax weight is
+                            // exp((zn - max) / gamma), and a 1-ulp change of zn is a 5e-4 relative change of the weight.
+                            zp = (K.far_ - zp) / (K.far_ - K.near_);
                         }
-                        if (save) {  // uniform
-                            const uint32_t m = __ballot_sync(0xffffffffu, emit);
-                            if (emit) {
-                                const int pos = __popc(m & lt);
-                                float4* dst = pb.recs + (size_t)(segbase + k) * BLK_F4 + pos;
-                                // closest-point barycentrics as the reference forms them: t_k + w_k (kernel.cu:638-641)
-                                const float u0 = fr.t0 + fr.w0, u1 = fr.t1 + fr.w1, u2 = fr.t2 + fr.w2;
-                                const uint32_t meta = (uint32_t)pix | ((tflags & SL_TIX) << 8) | ((tflags & SL_FRONT) ? (1u << 24) : 0u);
-                                dst[0] = make_float4(fr.D, fr.sign * fr.dx, fr.sign * fr.dy, zp);
-                                dst[32] = make_float4(u0, u1, u2, __uint_as_float(meta));
-                                dst[64] = make_float4(k0 / rc[2] / rc[2], k1 / rc[5] / rc[5], k2 / rc[8] / rc[8], 0.f);
-                            }
-                            if (lane == 0) pb.blk_hdr[segbase + k] = (uint32_t)s_list[j] | ((uint32_t)__popc(m) << 16);
-                        }
+                        sZ[slot] = zp;
+                        sD[slot] = fr.D;
+                        emit = zv;  // kernel.cu:592 drops every gradient of an out-of-range pair
                     }
+                    sT[slot] = tflags;
                 }
-                __syncthreads();
-
-                // ---------------- phase B: ordered per-pixel aggregation ----------------
-                {
-                    // faces of the sub-chunk whose rectangle meets this warp's 8x4 block (lane i <-> face ja + i)
-                    bool meets = false;
-                    if (ja + lane < jb) {
-                        const uint32_t g = s_geo[ja + lane];
-                        const int cx0 = (int)(g & 15u), w = (int)((g >> 4) & 31u);
-                        const int ry0 = (int)((g >> 9) & 15u), h = (int)((g >> 13) & 31u);
-                        meets = w > 0 && h > 0 && cx0 < bx0 + 8 && cx0 + w > bx0 && ry0 < by0 + 4 && ry0 + h > by0;
+                if (save) {  // uniform
+                    const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                    if (emit) {
+                        const int pos = __popc(m & lt);
+                        float4* dst = pb.recs + (size_t)(segbase + k) * BLK_F4 + pos;
+                        // closest-point barycentrics as the reference forms them: t_k + w_k (kernel.cu:638-641)
+                        const float u0 = fr.t0 + fr.w0, u1 = fr.t1 + fr.w1, u2 = fr.t2 + fr.w2;
+                        const uint32_t meta = (uint32_t)pix | ((tflags & SL_TIX) << 8) | ((tflags & SL_FRONT) ? (1u << 24) : 0u);
+                        dst[0] = make_float4(fr.D, fr.sign * fr.dx, fr.sign * fr.dy, zp);  // zp: depth (hard) / normalised depth (softmax)
+                        dst[32] = make_float4(u0, u1, u2, __uint_as_float(meta));
+                        // w_clip_k / z_k^2 (kernel.cu:624-627) through the record's precomputed 1 / z_k^2
+                        dst[64] = make_float4(k0 * rc[R_IZ2], k1 * rc[R_IZ2 + 1], k2 * rc[R_IZ2 + 2], 0.f);
                     }
-                    uint32_t fm = __ballot_sync(0xffffffffu, meets);
-                    while (fm) {
-                        const int i = __ffs(fm) - 1;
-                        fm &= fm - 1u;
-                        const int j = ja + i;
-                        const uint32_t geo = s_geo[j];
-                        const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
-                        const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
-                        const int dc = lcol - cx0, dr = lrow - ry0;
-                        float a_x = 0.f, a_y = 0.f, a_w = 0.f;
-                        bool contrib = false;
-                        if (live && (unsigned)dc < (unsigned)w && (unsigned)dr < (unsigned)h) {
-                            const int slot = (int)(s_boff[j] - kb0) * 32 + dr * w + dc;
-                            const uint32_t t = s_sT[slot];
-                            if (t & SL_VALID) {
-                                const float D = s_sD[slot];
-                                acc_a = (float)((double)acc_a * (1. - (double)D));  // kernel.cu:396
-                                if (t & SL_ZV) {
-                                    const int f = s_list[j];
-                                    const bool front = (t & SL_FRONT) != 0;
-                                    if (RGB == 0) {
-                                        const float zp = s_sZ[slot];
-                                        if (zp < zmin && (t & SL_INS) && (K.double_side || front)) {
-                                            zmin = zp;
-                                            fid = f;
-                                            const float* tp = tex_img + ((size_t)f * K.T2 + (t & SL_TIX)) * 3;
-                                            c0 = __ldg(tp); c1 = __ldg(tp + 1); c2 = __ldg(tp + 2);
-                                        }
-                                    } else if (front || K.double_side) {
-                                        const float zn = s_sZ[slot];
-                                        float ed = 1.f;
-                                        if (zn > smax) { ed = expf((smax - zn) / K.gamma); smax = zn; }
-                                        const float ez = expf((zn - smax) / K.gamma);
-                                        ssum = ed * ssum + ez * D;
-                                        const float a = ez * D;
-                                        if (a != 0.f || ed != 1.f) {  // else: c = 1*c + 0*texel, p2f terms 0 (exact)
-                                            a_x = a * gx; a_y = a * gy; a_w = a;
-                                            contrib = a != 0.f;
-                                            const float* tp = tex_img + ((size_t)f * K.T2 + (t & SL_TIX)) * 3;
-                                            c0 = ed * c0 + a * __ldg(tp);
-                                            c1 = ed * c1 + a * __ldg(tp + 1);
-                                            c2 = ed * c2 + a * __ldg(tp + 2);
-                                        }
-                                    }
+                    if (lane == 0) pb.blk_hdr[segbase + k] = (uint32_t)s_list[j] | ((uint32_t)__popc(m) << 16);
+                }
+            }
+        };
+
+        float own_x = 0.f, own_y = 0.f, own_w = 0.f;  // p2f partial sums: lane j owns face j of the current chunk
+
+        // ---------------- phase B: ordered per-pixel aggregation of faces [ja, jb) from slot buffer `buf`
+        auto phase_b = [&](int c, int ja, int jb, uint32_t kb0, int buf) {
+            const int cbeg = c * CHUNK;
+            const float* sD = s_sD + buf * SLOTS;
+            const float* sZ = s_sZ + buf * SLOTS;
+            const uint32_t* sT = s_sT + buf * SLOTS;
+            // faces of the sub-chunk whose rectangle meets this warp's 8x4 block (lane i <-> face ja + i)
+            bool meets = false;
+            if (ja + lane < jb) {
+                const uint32_t g = s_geo[ja + lane];
+                const int cx0 = (int)(g & 15u), w = (int)((g >> 4) & 31u);
+                const int ry0 = (int)((g >> 9) & 15u), h = (int)((g >> 13) & 31u);
+                meets = w > 0 && h > 0 && cx0 < bx0 + 8 && cx0 + w > bx0 && ry0 < by0 + 4 && ry0 + h > by0;
+            }
+            uint32_t fm = __ballot_sync(0xffffffffu, meets);
+            while (fm) {
+                const int i = __ffs(fm) - 1;
+                fm &= fm - 1u;
+                const int j = ja + i;
+                const uint32_t geo = s_geo[j];
+                const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
+                const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
+                const int dc = lcol - cx0, dr = lrow - ry0;
+                float a_x = 0.f, a_y = 0.f, a_w = 0.f;
+                bool contrib = false;
+                if (live && (unsigned)dc < (unsigned)w && (unsigned)dr < (unsigned)h) {
+                    const int slot = (int)(s_boff[j] - kb0) * 32 + dr * w + dc;
+                    const uint32_t t = sT[slot];
+                    if (t & SL_VALID) {
+                        const float D = sD[slot];
+                        acc_a = (float)((double)acc_a * (1. - (double)D));  // kernel.cu:396
+                        if (t & SL_ZV) {
+                            const int f = s_list[j];
+                            const bool front = (t & SL_FRONT) != 0;
+                            if (RGB == 0) {
+                                const float zp = sZ[slot];
+                                if (zp < zmin && (t & SL_INS) && (K.double_side || front)) {
+                                    zmin = zp;
+                                    fid = f;
+                                    const float* tp = tex_img + ((size_t)f * K.T2 + (t & SL_TIX)) * 3;
+                                    c0 = __ldg(tp); c1 = __ldg(tp + 1); c2 = __ldg(tp + 2);
                                 }
-                            }
-                        }
-                        if (RGB == 1 && p2f_acc != nullptr) {
-                            if (__any_sync(0xffffffffu, contrib)) {
-                                a_x = warp_sum(a_x); a_y = warp_sum(a_y); a_w = warp_sum(a_w);
-                                if (lane == j - cbeg) { own_x += a_x; own_y += a_y; own_w += a_w; }
+                            } else if (front || K.double_side) {
+                                const float zn = sZ[slot];
+                                float ed = 1.f;
+                                if (zn > smax) { ed = expf((smax - zn) / K.gamma); smax = zn; }
+                                const float ez = expf((zn - smax) / K.gamma);
+                                ssum = ed * ssum + ez * D;
+                                const float a = ez * D;
+                                if (a != 0.f || ed != 1.f) {  // else: c = 1*c + 0*texel, p2f terms 0 (exact)
+                                    a_x = a * gx; a_y = a * gy; a_w = a;
+                                    contrib = a != 0.f;
+                                    const float* tp = tex_img + ((size_t)f * K.T2 + (t & SL_TIX)) * 3;
+                                    c0 = ed * c0 + a * __ldg(tp);
+                                    c1 = ed * c1 + a * __ldg(tp + 1);
+                                    c2 = ed * c2 + a * __ldg(tp + 2);
+                                }
                             }
                         }
                     }
                 }
-                __syncthreads();  // slots free
-                ja = jb;
+                if (RGB == 1 && p2f_acc != nullptr) {
+                    if (__any_sync(0xffffffffu, contrib)) {
+                        a_x = warp_sum(a_x); a_y = warp_sum(a_y); a_w = warp_sum(a_w);
+                        if (lane == j - cbeg) { own_x += a_x; own_y += a_y; own_w += a_w; }
+                    }
+                }
             }
-            if (RGB == 1 && p2f_acc != nullptr && own_w != 0.f) {  // one global RED per (warp, face, component)
-                float* dst = p2f_acc + ((size_t)b * F + s_list[cbeg + lane]) * 4;
-                red_add_global(dst + 0, own_x);
-                red_add_global(dst + 1, own_y);
-                red_add_global(dst + 2, own_w);
+        };
+        // last face (exclusive) of the sub-chunk starting at ja inside chunk c: at most SUB_BLOCKS blocks
+        auto sub_end = [&](int c, int ja) {
+            const int cend = min(n, (c + 1) * CHUNK);
+            const uint32_t kb0 = s_boff[ja];
+            int jb = ja + 1;
+            while (jb < cend && s_boff[jb + 1] - kb0 <= (uint32_t)SUB_BLOCKS) ++jb;
+            return jb;
+        };
+
+        // Software pipeline over the segment's sub-chunks: A(0) | bar | B(0) A(1) | bar | B(1) A(2) | ... so the
+        // (pixel-imbalanced) aggregation of one sub-chunk overlaps the (balanced) geometry of the next and there is ONE
+        // CTA barrier per sub-chunk.  Record stage c % 2 is refilled once every phase A on chunk c is complete.
+        int c = 0, ja = 0, jb = sub_end(0, 0), buf = 0;
+        while (true) {
+            phase_a(c, ja, s_boff[ja], s_boff[jb], buf);
+            const int cend = min(n, (c + 1) * CHUNK);
+            const bool has_next = jb < n;
+            const bool chunk_switch = has_next && jb >= cend;  // the next sub-chunk starts chunk c + 1
+            if (chunk_switch) cp_async_wait<0>();               // ... whose records (the only group in flight) have landed
+            __syncthreads();  // A(cur) complete; B(prev) complete (its slot buffer is free); chunk c + 1 visible
+            if (chunk_switch) issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);  // stage c % 2 is free now
+            phase_b(c, ja, jb, s_boff[ja], buf);
+            if (jb >= cend) {  // chunk c fully aggregated: one global RED per (warp, face, component)
+                if (RGB == 1 && p2f_acc != nullptr && own_w != 0.f) {
+                    float* dst = p2f_acc + ((size_t)b * F + s_list[c * CHUNK + lane]) * 4;
+                    red_add_global(dst + 0, own_x);
+                    red_add_global(dst + 1, own_y);
+                    red_add_global(dst + 2, own_w);
+                }
+                own_x = own_y = own_w = 0.f;
             }
-            issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);  // stage st is free (barrier above); commits an empty group past the end
+            if (!has_next) break;
+            if (chunk_switch) ++c;
+            ja = jb;
+            jb = sub_end(c, ja);
+            buf ^= 1;
         }
         cp_async_wait<0>();
-        __syncthreads();  // segment done: s_list / s_geo / s_boff / s_rec reusable
+        __syncthreads();  // segment done: s_list / s_geo / s_boff / s_rec / slots reusable
     }
     if (tid == 0 && pb.cap > 0) pb.tile_head[tile_id] = head;
 
@@ -440,7 +544,6 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
         o2 = c2 == 0.f ? c2 : c2 / ssum;
         g0 = ssum; g1 = smax;
     }
-    const size_t np = (size_t)S * S;
     float v[4] = {o0, o1, o2, alpha};
     if (K.aa) {
 #pragma unroll
@@ -578,26 +681,49 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
         const uint32_t NB = __ldg(pb.blk_hdr + seg), next = __ldg(pb.blk_hdr + seg + 1);
         const uint32_t per = (NB + NWARP - 1) / NWARP;
         const uint32_t kbeg = min(NB, warp * per), kend = min(NB, kbeg + per);
-        for (uint32_t k = kbeg; k < kend; ++k) {
-            const uint32_t hdr = __ldg(pb.blk_hdr + seg + 2 + k);
-            const int cnt = (int)(hdr >> 16);
-            if (cnt == 0) continue;  // warp-uniform
-            const int f = (int)(hdr & 0xffffu);
+        const uint32_t* hdrs = pb.blk_hdr + seg + 2;
+        // The warp streams the records of its block range 32 at a time: blocks are only partly filled (survivors
+        // of 32 candidates), so each step packs the unread records of up to 4 consecutive same-face blocks onto the
+        // lanes -- (k, o) = current block and records of it already consumed.
+        uint32_t k = kbeg;
+        int o = 0;
+        while (k < kend) {
+            uint32_t myh = 0;
+            if (lane < 4 && k + lane < kend) myh = __ldg(hdrs + k + lane);
+            const uint32_t h0 = __shfl_sync(0xffffffffu, myh, 0), h1 = __shfl_sync(0xffffffffu, myh, 1);
+            const uint32_t h2 = __shfl_sync(0xffffffffu, myh, 2), h3 = __shfl_sync(0xffffffffu, myh, 3);
+            const int a0 = (int)(h0 >> 16) - o;
+            if (a0 <= 0) { ++k; o = 0; continue; }  // block exhausted / empty (warp-uniform)
+            const int f = (int)(h0 & 0xffffu);
+            // records available in the following blocks while they belong to the same face (an empty block is transparent)
+            int a1 = 0, a2 = 0, a3 = 0, nchain = 1;
+            if (k + 1 < kend && ((h1 >> 16) == 0 || (int)(h1 & 0xffffu) == f)) {
+                a1 = (int)(h1 >> 16); nchain = 2;
+                if (k + 2 < kend && ((h2 >> 16) == 0 || (int)(h2 & 0xffffu) == f)) {
+                    a2 = (int)(h2 >> 16); nchain = 3;
+                    if (k + 3 < kend && ((h3 >> 16) == 0 || (int)(h3 & 0xffffu) == f)) { a3 = (int)(h3 >> 16); nchain = 4; }
+                }
+            }
+            const int p1 = a0, p2 = a0 + a1, p3 = p2 + a2, p4 = p3 + a3;
             if (f != cur_f) { flush(); cur_f = f; }
-            if (lane < cnt) {
-                const float4* src = pb.recs + (size_t)(seg + 2 + k) * BLK_F4 + lane;
+            if (lane < p4) {
+                int bi, pos;
+                if (lane < p1) { bi = 0; pos = lane + o; }
+                else if (lane < p2) { bi = 1; pos = lane - p1; }
+                else if (lane < p3) { bi = 2; pos = lane - p2; }
+                else { bi = 3; pos = lane - p3; }
+                const float4* src = pb.recs + (size_t)(seg + 2 + k + bi) * BLK_F4 + pos;
                 const float4 r0 = __ldg(src), r1 = __ldg(src + 32), r2 = __ldg(src + 64);
-                const float D = r0.x, sdx = r0.y, sdy = r0.z, zp = r0.w;
+                const float D = r0.x, sdx = r0.y, sdy = r0.z, zn = r0.w;  // zn: normalised depth exactly as the forward formed it
                 const uint32_t meta = __float_as_uint(r1.w);
                 const int pix = (int)(meta & 0xffu), tix = (int)((meta >> 8) & 0xffffu);
                 const bool front = (meta >> 24) & 1u;
                 const float* sp = &s_pix[0][pix];
                 const float g3 = sp[3 * 256];
                 const float one_m_a = 1 - sp[7 * 256];
-                // g3 * ((1 - alpha) / max(1 - D, 1e-6)) (kernel.cu:584); zero cases answered directly
-                float Cxy = (one_m_a == 0.f || g3 == 0.f)
-                                ? g3 * one_m_a
-                                : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - D), 1e-6)));
+                // g3 * ((1 - alpha) / max(1 - D, 1e-6)) (kernel.cu:584), in fp32 (the reference promotes to double;
+                // gradients are compared at 1e-4, see DESIGN.md "backward arithmetic")
+                float Cxy = (one_m_a == 0.f || g3 == 0.f) ? g3 * one_m_a : g3 * __fdividef(one_m_a, fmaxf(1 - D, 1e-6f));
                 if (RGB == 0) {
                     if ((float)f == sp[9 * 256]) {  // aggrs[1] = winning face id (:596)
                         if (TEXGRAD) {
@@ -610,8 +736,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                 } else if (front || K.double_side) {
                     const float g0 = sp[0], g1 = sp[1 * 256], g2 = sp[2 * 256];
                     if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
-                        const float zn = (K.far_ - zp) / (K.far_ - K.near_);
-                        const float s = D * expf((zn - sp[9 * 256]) / K.gamma) / sp[8 * 256];  // :608
+                        const float s = __fdividef(D * expf((zn - sp[9 * 256]) * K.r_gamma), sp[8 * 256]);  // :608
                         if (s != 0.f) {
                             const size_t to = ((size_t)f * K.T2 + tix) * 3;
                             if (TEXGRAD) {
@@ -625,8 +750,9 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                             Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * 256]);
                             Crgb *= s;
                             if (Crgb != 0.f) {
-                                Cxy += Crgb / D;
-                                const float Cz = Crgb / K.gamma / (K.near_ - K.far_) * zp * zp;  // :624
+                                Cxy += __fdividef(Crgb, D);
+                                const float zp = K.far_ - zn * (K.far_ - K.near_);
+                                const float Cz = Crgb * K.r_gamma * K.r_nf * zp * zp;  // :624
                                 acc[2] += Cz * r2.x;
                                 acc[5] += Cz * r2.y;
                                 acc[8] += Cz * r2.z;
@@ -634,14 +760,25 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                         }
                     }
                 }
-                Cxy *= D * (1 - D) / K.sigma;  // :632
-                const float q = 2 * Cxy;       // :640 (the sign rides in sdx / sdy)
+                Cxy *= D * (1 - D) * K.r_sigma;  // :632
+                const float q = 2 * Cxy;          // :640 (the sign rides in sdx / sdy)
                 acc[0] += q * r1.x * sdx;
                 acc[1] += q * r1.x * sdy;
                 acc[3] += q * r1.y * sdx;
                 acc[4] += q * r1.y * sdy;
                 acc[6] += q * r1.z * sdx;
                 acc[7] += q * r1.z * sdy;
+            }
+            // advance the stream by min(32, p4) records: blocks consumed completely, then a partial one
+            {
+                int left = min(32, p4), i = 0;
+                const int av[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (i == q && q < nchain && left >= av[q]) { left -= av[q]; ++i; }
+                }
+                k += (uint32_t)i;
+                o = (i == 0) ? o + left : ((i < nchain) ? left : 0);
             }
         }
         seg = next;
