@@ -38,7 +38,7 @@ def test_streamed_backward_matches_recompute_and_oracle(rgb, B, subdiv, tex_res,
     fv, tex = scene(B, subdiv, tex_res, seed=31 + image_size)
     g = np.random.default_rng(5).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
     ref = run_oracle(fv, tex, image_size, True, rgb, g)
-    full = _run(fv, tex, image_size, rgb, g, 8.0)     # everything saved
+    full = _run(fv, tex, image_size, rgb, g, 32.0)    # everything saved
     none = _run(fv, tex, image_size, rgb, g, 0.0)     # no pair buffer: recompute backward
     part = _run(fv, tex, image_size, rgb, g, 0.7)     # buffer too small: some tiles saved, the rest recomputed
     tiny = _run(fv, tex, image_size, rgb, g, 1e-4)    # nothing fits

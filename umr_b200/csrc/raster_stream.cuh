@@ -30,7 +30,13 @@ namespace umr {
 
 constexpr int CB = 64;             // coarse bin side in pixels (4 x 4 tiles)
 constexpr int LCAP = 512;          // coarse-list window == longest tile-list segment held in shared memory
-constexpr int SUB_BLOCKS = 64;     // 32-candidate blocks per sub-chunk
+#ifndef UMR_SUB_BLOCKS
+#define UMR_SUB_BLOCKS 64
+#endif
+#ifndef UMR_FWD2_CTAS
+#define UMR_FWD2_CTAS 3
+#endif
+constexpr int SUB_BLOCKS = UMR_SUB_BLOCKS;     // 32-candidate blocks per sub-chunk
 constexpr int SLOTS = SUB_BLOCKS * 32;
 constexpr uint32_t SEG_NONE = 0xffffffffu;
 constexpr int32_t TILE_EMPTY = -1, TILE_UNSAVED = -2;
@@ -38,6 +44,11 @@ constexpr int BLK_F4 = 96;         // float4 per block: 3 planes x 32 records
 
 // slot / record flag bits
 constexpr uint32_t SL_VALID = 1u << 31, SL_ZV = 1u << 30, SL_FRONT = 1u << 29, SL_INS = 1u << 28, SL_TIX = 0xffffu;
+
+// c_rcpw[w] = ceil(65536 / w): (l * c_rcpw[w]) >> 16 == l / w exactly for l < 1024, w <= 32
+__constant__ uint32_t c_rcpw[33] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554,
+                                    5958,  5462,  5042,  4682,  4370,  4096,  3856,  3641, 3450, 3277, 3121,
+                                    2979,  2850,  2731,  2622,  2521,  2428,  2341,  2260, 2185, 2115, 2048};
 
 struct PairBuf {
     uint32_t* ctrl;      // [0] block cursor (== blocks wanted, may exceed cap), [1] tiles left unsaved
@@ -98,7 +109,7 @@ __global__ void __launch_bounds__(CTA) k_bin_coarse(const float4* __restrict__ b
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int RGB>
-__global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
+__global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
                                                         const uint16_t* __restrict__ clist, const int* __restrict__ ccount,
                                                         const float* __restrict__ textures, float* __restrict__ images,
                                                         float* __restrict__ colors_hi, float* __restrict__ aggrs,
@@ -359,13 +370,27 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
             float* sD = s_sD + buf * SLOTS;
             float* sZ = s_sZ + buf * SLOTS;
             uint32_t* sT = s_sT + buf * SLOTS;
+            // each warp owns a contiguous range of the sub-chunk's blocks: the face index only moves forward and the
+            // face's rectangle is decoded once per face, not once per block
+            const uint32_t nblk = kb1 - kb0, per = (nblk + NWARP - 1) / NWARP;
+            const uint32_t kbeg = kb0 + min(nblk, warp * per), kend = kb0 + min(nblk, (warp + 1) * per);
             int j = ja;
-            for (uint32_t k = kb0 + warp; k < kb1; k += NWARP) {
-                while (s_boff[j + 1] <= k) ++j;  // warp-uniform, monotone
-                const uint32_t geo = s_geo[j];
-                const int cx0 = (int)(geo & 15u), w = (int)((geo >> 4) & 31u);
-                const int ry0 = (int)((geo >> 9) & 15u), h = (int)((geo >> 13) & 31u);
-                const int local = (int)(k - s_boff[j]) * 32 + lane;
+            uint32_t jnext = s_boff[ja + 1], jbase = kb0;  // blocks of face j: [jbase, jnext)
+            int cx0 = 0, w = 0, ry0 = 0, size = 0;
+            uint32_t rcpw = 0;
+            bool fresh = true;
+            for (uint32_t k = kbeg; k < kend; ++k) {
+                while (jnext <= k) { ++j; jnext = s_boff[j + 1]; fresh = true; }  // warp-uniform, monotone
+                if (fresh) {
+                    const uint32_t geo = s_geo[j];
+                    cx0 = (int)(geo & 15u); w = (int)((geo >> 4) & 31u);
+                    ry0 = (int)((geo >> 9) & 15u);
+                    size = w * (int)((geo >> 13) & 31u);
+                    rcpw = c_rcpw[w];
+                    jbase = s_boff[j];
+                    fresh = false;
+                }
+                const int local = (int)(k - jbase) * 32 + lane;
                 const int slot = (int)(k - kb0) * 32 + lane;
                 const float* rc = chunk + (j - cbeg) * REC_F;
                 uint32_t tflags = 0;
@@ -373,9 +398,8 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_fwd2(const float* __restrict_
                 Frag fr;
                 float k0 = 0.f, k1 = 0.f, k2 = 0.f, zp = 0.f;
                 int pix = 0;
-                if (local < w * h) {
-                    const uint32_t rcpw = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // exact floor(l / w): l < 1024, w <= 32
-                    const int lr = (int)(((uint32_t)local * rcpw) >> 16);
+                if (local < size) {
+                    const int lr = (int)(((uint32_t)local * rcpw) >> 16);  // exact floor(local / w): local < 1024, w <= 32
                     const int col = cx0 + (local - lr * w), row = ry0 + lr;
                     pix = row * TILE + col;
                     if (fragment(rc, s_xp[col], s_yp[row], K.thr, K.sigma, fr)) {
@@ -685,23 +709,30 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
         // The warp streams the records of its block range 32 at a time: blocks are only partly filled (survivors
         // of 32 candidates), so each step packs the unread records of up to 4 consecutive same-face blocks onto the
         // lanes -- (k, o) = current block and records of it already consumed.
-        uint32_t k = kbeg;
+        // block headers of the warp's range: ONE coalesced load per 32 blocks, kept in registers and read with shuffles
+        // (a header load inside the loop would put a second global-memory latency in front of every record load)
+        uint32_t k = kbeg, kwin = kbeg;
+        uint32_t hw = (kbeg + lane < kend) ? __ldg(hdrs + kbeg + lane) : 0u;
         int o = 0;
         while (k < kend) {
-            uint32_t myh = 0;
-            if (lane < 4 && k + lane < kend) myh = __ldg(hdrs + k + lane);
-            const uint32_t h0 = __shfl_sync(0xffffffffu, myh, 0), h1 = __shfl_sync(0xffffffffu, myh, 1);
-            const uint32_t h2 = __shfl_sync(0xffffffffu, myh, 2), h3 = __shfl_sync(0xffffffffu, myh, 3);
+            if (k >= kwin + 32u) {  // warp-uniform
+                kwin = k;
+                hw = (k + lane < kend) ? __ldg(hdrs + k + lane) : 0u;
+            }
+            const uint32_t wend = min(kend, kwin + 32u);  // chains stop at the header window
+            const int rel = (int)(k - kwin);
+            const uint32_t h0 = __shfl_sync(0xffffffffu, hw, rel), h1 = __shfl_sync(0xffffffffu, hw, (rel + 1) & 31);
+            const uint32_t h2 = __shfl_sync(0xffffffffu, hw, (rel + 2) & 31), h3 = __shfl_sync(0xffffffffu, hw, (rel + 3) & 31);
             const int a0 = (int)(h0 >> 16) - o;
             if (a0 <= 0) { ++k; o = 0; continue; }  // block exhausted / empty (warp-uniform)
             const int f = (int)(h0 & 0xffffu);
             // records available in the following blocks while they belong to the same face (an empty block is transparent)
             int a1 = 0, a2 = 0, a3 = 0, nchain = 1;
-            if (k + 1 < kend && ((h1 >> 16) == 0 || (int)(h1 & 0xffffu) == f)) {
+            if (k + 1 < wend && ((h1 >> 16) == 0 || (int)(h1 & 0xffffu) == f)) {
                 a1 = (int)(h1 >> 16); nchain = 2;
-                if (k + 2 < kend && ((h2 >> 16) == 0 || (int)(h2 & 0xffffu) == f)) {
+                if (k + 2 < wend && ((h2 >> 16) == 0 || (int)(h2 & 0xffffu) == f)) {
                     a2 = (int)(h2 >> 16); nchain = 3;
-                    if (k + 3 < kend && ((h3 >> 16) == 0 || (int)(h3 & 0xffffu) == f)) { a3 = (int)(h3 >> 16); nchain = 4; }
+                    if (k + 3 < wend && ((h3 >> 16) == 0 || (int)(h3 & 0xffffu) == f)) { a3 = (int)(h3 >> 16); nchain = 4; }
                 }
             }
             const int p1 = a0, p2 = a0 + a1, p3 = p2 + a2, p4 = p3 + a3;

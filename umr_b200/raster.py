@@ -88,7 +88,7 @@ def collect_profile(sink):
 # --- pair buffer (saved (pixel, face) records streamed by the backward; include/umr_b200.h) -------------
 # Budget in candidate pairs per raster pixel (measured: 2.7 at F=1280, 4.8 at F=5120) and an
 # upper bound on one render's buffer; tiles that do not fit are recomputed by the backward (same results).
-PAIR_CAND_PER_PIXEL = float(os.environ.get("UMR_PAIR_CAND_PER_PIXEL", "6.0"))
+PAIR_CAND_PER_PIXEL = float(os.environ.get("UMR_PAIR_CAND_PER_PIXEL", "8.0"))
 PAIR_MAX_BYTES = int(float(os.environ.get("UMR_PAIR_MAX_GB", "24")) * (1 << 30))
 
 
