@@ -90,7 +90,10 @@ __device__ __forceinline__ uint32_t ubox_key(float v) {
 // grid (ceil(F/256), B): every block belongs to one image.  Also accumulates the image's UNION cull box
 // ubox[b] = {max xhi, max -xlo, max yhi, max -ylo} (keys) so tiles outside it skip the face scan.
 __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ fv, float* __restrict__ rec,
-                                              float4* __restrict__ box, uint32_t* __restrict__ ubox, int F, float r) {
+                                              float4* __restrict__ box, uint32_t* __restrict__ ubox, int F, float r,
+                                              const uint32_t* __restrict__ only_if_nonzero = nullptr) {
+    // backward with a pair buffer: the records are only needed by the recompute fallback -- skip when no tile needs it
+    if (only_if_nonzero != nullptr && __ldg(only_if_nonzero) == 0u) return;
     const int fidx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = fidx < F;
     const int i = blockIdx.y * F + (valid ? fidx : F - 1);  // clamp: the tail threads redo the last face
@@ -473,10 +476,9 @@ __host__ __device__ inline size_t smem_list_off(int F) {
 // barrier per piece turns the per-warp counts into list offsets.  Returns the list length (uniform).
 __device__ __forceinline__ int build_tile_list(const float4* __restrict__ box, int F, float tx_first,
                                                float tx_last, float ty_bot, float ty_top, float4* s_box,
-                                               uint16_t* list, int* s_warp_cnt, uint64_t* bar) {
+                                               uint16_t* list, int* s_warp_cnt, uint64_t* bar, uint32_t& phase) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int total = 0;
-    uint32_t phase = 0;
     for (int base = 0; base < F; base += BOX_PIECE) {
         const int P = min(BOX_PIECE, F - base);
         if (tid == 0) {
@@ -557,14 +559,17 @@ __device__ __forceinline__ PixelMap map_pixel(int S) {
 
 // tile extents in pixel-centre coordinates (monotone in the index, so the cull test is conservative);
 // four threads compute one division each and broadcast through shared memory
-__device__ __forceinline__ void tile_extents(int S, float* s_ext, int tile = TILE) {
+__device__ __forceinline__ void tile_extents_at(int S, float* s_ext, int tile, int bx, int by) {
     const int t = threadIdx.x;
     if (t < 4) {
-        const int x_last_i = min((int)blockIdx.x * tile + tile - 1, S - 1);
-        const int y_last_i = min((int)blockIdx.y * tile + tile - 1, S - 1);
-        const int i = t == 0 ? blockIdx.x * tile : t == 1 ? x_last_i : t == 2 ? S - 1 - y_last_i : S - 1 - blockIdx.y * tile;
+        const int x_last_i = min(bx * tile + tile - 1, S - 1);
+        const int y_last_i = min(by * tile + tile - 1, S - 1);
+        const int i = t == 0 ? bx * tile : t == 1 ? x_last_i : t == 2 ? S - 1 - y_last_i : S - 1 - by * tile;
         s_ext[t] = pixel_coord(i, S);  // 0: x first, 1: x last, 2: y bottom, 3: y top
     }
+}
+__device__ __forceinline__ void tile_extents(int S, float* s_ext, int tile = TILE) {
+    tile_extents_at(S, s_ext, tile, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // =============================================================================================
@@ -603,9 +608,10 @@ __global__ void __launch_bounds__(CTA, GEN ? 3 : 4) k_raster_fwd(const float* __
 
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
+    uint32_t bar_phase = 0;
     const int n = tile_outside_union(ubox, b, s_ext)
                       ? 0
-                      : build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
+                      : build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar, bar_phase);
     // (build_tile_list ends with __syncthreads: the list is visible)
 
     // pixel state (kernel.cu:335-348)
@@ -856,7 +862,8 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
     if (tile_outside_union(ubox, b, s_ext)) return;  // uniform
-    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
+    uint32_t bar_phase = 0;
+    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar, bar_phase);
     if (n == 0) return;  // uniform
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
@@ -1174,27 +1181,19 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
     return true;
 }
 
+// One PT x PT tile of the recompute backward (bx, by, b = tile column / row / image).  Every early exit is CTA-uniform.
+// `bar_phase` carries the mbarrier parity across the tiles a CTA processes (list-driven launch).
 template <int RGB, bool TEXGRAD>
-__global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all,
-                                                             const float4* __restrict__ box_all,
-                                                             const float* __restrict__ textures,
-                                                             const float* __restrict__ colors_hi,
-                                                             const float* __restrict__ aggrs,
-                                                             const float* __restrict__ grad_images,
-                                                             float* __restrict__ grad_faces,
-                                                             float* __restrict__ grad_tex,
-                                                             const uint32_t* __restrict__ ubox, Consts K,
-                                                             const int32_t* __restrict__ tile_head) {
-    // With a pair buffer this kernel is only the FALLBACK for tiles the forward could not save (tile_head ==
-    // TILE_UNSAVED, -2); every other tile is streamed by k_raster_bwd2 (raster_stream.cuh).
-    if (tile_head != nullptr &&
-        __ldg(tile_head + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) != -2)
-        return;
+__device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
+                                               const float* __restrict__ textures, const float* __restrict__ colors_hi,
+                                               const float* __restrict__ aggrs, const float* __restrict__ grad_images,
+                                               float* __restrict__ grad_faces, float* __restrict__ grad_tex,
+                                               const uint32_t* __restrict__ ubox, const Consts& K, int bx, int by, int b,
+                                               uint64_t* s_bar_p, uint32_t& bar_phase) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_rec = reinterpret_cast<float*>(smem_raw);
     float4* s_box = reinterpret_cast<float4*>(smem_raw + smem_box_off());
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_raw + smem_list_off(K.F));
-    __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[NWARP];
     __shared__ float s_ext[4];
     // PT x PT pixel tile.  PT = 32 (4x the pairs per chunk) was measured 27 % slower than 16 on C2.
@@ -1204,24 +1203,20 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
     __shared__ int s_off[CHUNK + 1];                  // prefix sums of the rectangle sizes
     __shared__ uint32_t s_geo[CHUNK];                 // cx0 | w<<8 | ry0<<16 | rcp(w)<<... (see below)
     __shared__ uint32_t s_rcpw[CHUNK];
+    uint64_t& s_bar = *s_bar_p;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int b = blockIdx.z;
     const int S = K.S, F = K.F;
-    const int x0 = blockIdx.x * PT, y0 = blockIdx.y * PT;
+    const int x0 = bx * PT, y0 = by * PT;
 
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        fence_mbar_init();
-    }
-    tile_extents(S, s_ext, PT);
+    tile_extents_at(S, s_ext, PT, bx, by);
     if (tid < PT) s_xp[tid] = pixel_coord(x0 + tid, S);
     else if (tid < 2 * PT) s_yp[tid - PT] = pixel_coord(S - 1 - (y0 + tid - PT), S);
     __syncthreads();
     if (tile_outside_union(ubox, b, s_ext)) return;  // uniform
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar);
+    const int n = build_tile_list(box, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, s_list, s_warp_cnt, &s_bar, bar_phase);
     if (n == 0) return;  // uniform
 
     const int nchunk = (n + CHUNK - 1) / CHUNK;
@@ -1362,6 +1357,53 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
         __syncthreads();  // everyone is done with stage st
         issue_chunk(rec_img, s_list, n, c + NSTAGE, s_rec);
     }
+    cp_async_wait<0>();
+    __syncthreads();  // shared memory reusable by the next tile of this CTA (list-driven launch)
+}
+
+
+// full grid: one CTA per tile (no pair buffer: every tile is recomputed)
+template <int RGB, bool TEXGRAD>
+__global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
+                                                             const float* __restrict__ textures, const float* __restrict__ colors_hi,
+                                                             const float* __restrict__ aggrs, const float* __restrict__ grad_images,
+                                                             float* __restrict__ grad_faces, float* __restrict__ grad_tex,
+                                                             const uint32_t* __restrict__ ubox, Consts K) {
+    __shared__ uint64_t s_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    uint32_t phase = 0;  // (bwd_pairs_tile synchronises the CTA before the barrier is first used)
+    bwd_pairs_tile<RGB, TEXGRAD>(rec_all, box_all, textures, colors_hi, aggrs, grad_images, grad_faces, grad_tex, ubox, K,
+                                 (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, &s_bar, phase);
+}
+
+// list-driven: with a pair buffer, only the tiles the forward could NOT save are recomputed.  The forward appended
+// their ids to `ulist` (count in *ucount); a small persistent grid walks the list, so a render whose tiles were all
+// saved pays one near-empty launch instead of one CTA per tile (35 us at C2 with the full grid).
+template <int RGB, bool TEXGRAD>
+__global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs_list(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
+                                                                  const float* __restrict__ textures, const float* __restrict__ colors_hi,
+                                                                  const float* __restrict__ aggrs, const float* __restrict__ grad_images,
+                                                                  float* __restrict__ grad_faces, float* __restrict__ grad_tex,
+                                                                  const uint32_t* __restrict__ ubox, Consts K,
+                                                                  const uint32_t* __restrict__ ucount, const int32_t* __restrict__ ulist,
+                                                                  int tiles_x, int tiles_y) {
+    const uint32_t nu = __ldg(ucount);
+    if (blockIdx.x >= nu) return;
+    __shared__ uint64_t s_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    uint32_t phase = 0;
+    for (uint32_t i = blockIdx.x; i < nu; i += gridDim.x) {
+        const int t = __ldg(ulist + i);
+        const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+        bwd_pairs_tile<RGB, TEXGRAD>(rec_all, box_all, textures, colors_hi, aggrs, grad_images, grad_faces, grad_tex, ubox, K,
+                                     bx, by, b, &s_bar, phase);
+    }
 }
 
 }  // namespace umr
@@ -1388,7 +1430,7 @@ extern "C" size_t umr_raster_pair_buffer_bytes(int32_t B, int32_t image_size, in
 // device pointers into the caller's pair buffer (cap == 0: no saving)
 static PairBuf make_pairbuf(const UmrRasterParams* p, int S) {
     PairBuf pb;
-    pb.ctrl = nullptr; pb.tile_head = nullptr; pb.blk_hdr = nullptr; pb.recs = nullptr; pb.cap = 0;
+    pb.ctrl = nullptr; pb.tile_head = nullptr; pb.ulist = nullptr; pb.blk_hdr = nullptr; pb.recs = nullptr; pb.cap = 0;
     if (!p->pair_buffer || p->pair_buffer_bytes == 0 || ((uintptr_t)p->pair_buffer & 255) != 0) return pb;
     size_t cap = pair_capacity(p->batch_size, S, (size_t)p->pair_buffer_bytes);
     if (cap > 0x7fff0000u) cap = 0x7fff0000u;
@@ -1397,6 +1439,7 @@ static PairBuf make_pairbuf(const UmrRasterParams* p, int S) {
     char* base = (char*)p->pair_buffer;
     pb.ctrl = (uint32_t*)(base + L.ctrl_off);
     pb.tile_head = (int32_t*)(base + L.head_off);
+    pb.ulist = (int32_t*)(base + L.ulist_off);
     pb.blk_hdr = (uint32_t*)(base + L.hdr_off);
     pb.recs = (float4*)(base + L.rec_off);
     pb.cap = (uint32_t)cap;
@@ -1474,6 +1517,8 @@ static int ensure_smem_attrs() {
     UMR_SET((k_raster_bwd<1, false, true>)) UMR_SET((k_raster_bwd<1, true, true>))
     UMR_SET((k_raster_bwd_pairs<0, false>)) UMR_SET((k_raster_bwd_pairs<0, true>))
     UMR_SET((k_raster_bwd_pairs<1, false>)) UMR_SET((k_raster_bwd_pairs<1, true>))
+    UMR_SET((k_raster_bwd_pairs_list<0, false>)) UMR_SET((k_raster_bwd_pairs_list<0, true>))
+    UMR_SET((k_raster_bwd_pairs_list<1, false>)) UMR_SET((k_raster_bwd_pairs_list<1, true>))
 #undef UMR_SET
     done[dev] = true;
     return 0;
@@ -1596,7 +1641,14 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     // the workspace is scratch (another render may have used it since forward): rebuild the records
     cudaError_t e = cudaMemsetAsync(ubox, 0, (size_t)B * 4 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return (int)e;
-    k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, r);
+    const bool gen = is_generic(p);
+    static const bool no_stream = [] {  // UMR_BWD_IMPL=recompute ignores the pair buffer (A/B testing)
+        const char* e = getenv("UMR_BWD_IMPL");
+        return e && e[0] == 'r' && e[1] == 'e' && e[2] == 'c';
+    }();
+    const PairBuf pb = (gen || no_stream) ? PairBuf{nullptr, nullptr, nullptr, nullptr, nullptr, 0u} : make_pairbuf(p, K.S);
+    // (with a pair buffer the records only serve the recompute fallback: k_prep returns at once when no tile needs it)
+    k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, r, pb.cap > 0 ? pb.ctrl + 1 : nullptr);
     count_launch();
     e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
     if (e != cudaSuccess) return (int)e;
@@ -1622,21 +1674,21 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
                 k_raster_bwd2<RGBM, TG><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images,  \
                                                                         grad_faces, grad_textures, K, pb);    \
             }                                                                                                 \
-            k_raster_bwd_pairs<RGBM, TG><<<grid_pairs, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
-                                                                      grad_images, grad_faces, grad_textures, ubox, K,  \
-                                                                      pb.cap > 0 ? pb.tile_head : nullptr);   \
+            if (pb.cap > 0)                                                                                   \
+                k_raster_bwd_pairs_list<RGBM, TG><<<list_grid, CTA, smem, stream>>>(                          \
+                    rec, box, textures, soft_colors, aggrs_info, grad_images, grad_faces, grad_textures, ubox, K, \
+                    pb.ctrl + 1, pb.ulist, (int)grid_pairs.x, (int)grid_pairs.y);                             \
+            else                                                                                              \
+                k_raster_bwd_pairs<RGBM, TG><<<grid_pairs, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
+                                                                      grad_images, grad_faces, grad_textures, ubox, K); \
         }                                                                                                     \
         else                                                                                                  \
             k_raster_bwd<RGBM, TG, false><<<grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, \
                                                                        grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
-    const bool gen = is_generic(p);
-    static const bool no_stream = [] {  // UMR_BWD_IMPL=recompute ignores the pair buffer (A/B testing)
-        const char* e = getenv("UMR_BWD_IMPL");
-        return e && e[0] == 'r' && e[1] == 'e' && e[2] == 'c';
-    }();
-    const PairBuf pb = (gen || no_stream) ? PairBuf{nullptr, nullptr, nullptr, nullptr, 0u} : make_pairbuf(p, K.S);
     const dim3 grid_pairs((K.S + PT - 1) / PT, (K.S + PT - 1) / PT, B);
+    const size_t ntiles = (size_t)grid_pairs.x * grid_pairs.y * B;
+    const unsigned list_grid = (unsigned)(ntiles < 444 ? ntiles : 444);  // 3 CTAs x 148 SMs walk the unsaved-tile list
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();
     if (softmax) {

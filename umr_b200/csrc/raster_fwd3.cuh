@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
             if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
                 s_save = 0;  // does not fit: the whole tile falls back to the recompute backward
                 head = TILE_UNSAVED;
-                atomicAdd(pb.ctrl + 1, 1u);
+                pb.ulist[atomicAdd(pb.ctrl + 1, 1u)] = (int32_t)tile_id;
             } else {
                 pb.blk_hdr[base] = NBw;
                 pb.blk_hdr[base + 1] = SEG_NONE;

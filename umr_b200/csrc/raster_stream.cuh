@@ -53,20 +53,22 @@ __constant__ uint32_t c_rcpw[33] = {0,     65536, 32768, 21846, 16384, 13108, 10
 struct PairBuf {
     uint32_t* ctrl;      // [0] block cursor (== blocks wanted, may exceed cap), [1] tiles left unsaved
     int32_t* tile_head;  // [B * tiles]: first segment (block index), TILE_EMPTY or TILE_UNSAVED
+    int32_t* ulist;      // [B * tiles]: ids of the unsaved tiles (count = ctrl[1]), walked by the recompute fallback
     uint32_t* blk_hdr;   // [cap]: per block  face | count << 16 ; per segment  [base] = #blocks, [base+1] = next
     float4* recs;        // [cap][3][32]
     uint32_t cap;        // blocks
 };
 
 struct PairBufLayout {
-    size_t ctrl_off, head_off, hdr_off, rec_off, total;
+    size_t ctrl_off, head_off, ulist_off, hdr_off, rec_off, total;
 };
 inline PairBufLayout pair_layout(int B, int S, size_t cap_blocks) {
     PairBufLayout L;
     const size_t nt = (size_t)((S + TILE - 1) / TILE) * ((S + TILE - 1) / TILE) * B;
     L.ctrl_off = 0;
     L.head_off = 256;
-    L.hdr_off = L.head_off + align256(nt * sizeof(int32_t));
+    L.ulist_off = L.head_off + align256(nt * sizeof(int32_t));
+    L.hdr_off = L.ulist_off + align256(nt * sizeof(int32_t));
     L.rec_off = L.hdr_off + align256(cap_blocks * sizeof(uint32_t));
     L.total = L.rec_off + cap_blocks * (size_t)BLK_F4 * sizeof(float4);
     return L;
@@ -99,9 +101,10 @@ __global__ void __launch_bounds__(CTA) k_bin_coarse(const float4* __restrict__ b
     __syncthreads();
     const size_t cidx = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     int n = 0;
+    uint32_t bar_phase = 0;
     if (!tile_outside_union(ubox, b, s_ext))
         n = build_tile_list(box_all + (size_t)b * F, F, s_ext[0], s_ext[1], s_ext[2], s_ext[3], s_box, clist + cidx * F,
-                            s_warp_cnt, &s_bar);
+                            s_warp_cnt, &s_bar, bar_phase);
     if (threadIdx.x == 0) ccount[cidx] = n;
 }
 
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
             if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
                 s_save = 0;  // does not fit: the whole tile falls back to the recompute backward
                 head = TILE_UNSAVED;
-                atomicAdd(pb.ctrl + 1, 1u);
+                pb.ulist[atomicAdd(pb.ctrl + 1, 1u)] = (int32_t)tile_id;
             } else {
                 pb.blk_hdr[base] = NBw;
                 pb.blk_hdr[base + 1] = SEG_NONE;
