@@ -216,10 +216,11 @@ class Workload:
         self.mean_shape.grad = None
         self.texture.grad = None
         verts = self.mean_shape[None] + delta
-        tex = self.texture[None].expand(B, -1, -1, -1)
+        tex = self.texture[None]          # [1,F,T2,3]: batch-shared texture parameter (no repeat(B) copies)
         images, _, _ = self.renderer(verts, self.faces, cams, tex)
-        alpha, rgb = images[:, 3], images[:, :3]
-        loss = 2.5 * loss_utils.neg_iou_loss(alpha, masks) + 3.0 * loss_utils.texture_loss_masks(rgb, imgs, masks, alpha)
+        # 2.5 * neg_iou_loss(alpha, masks) + 3.0 * texture_loss_masks(rgb, imgs, masks, alpha) (train_s2.py:49-59 weights),
+        # fused: one reduction forward, one kernel backward (tests/test_losses_gpu.py checks it against the composition)
+        loss = loss_utils.mask_texture_loss(images, imgs, masks, 2.5, 3.0)
         loss.backward()
         if reduce:
             self.reducer()  # N>1: ONE NCCL all-reduce of the flat [V*3 + F*T2*3] gradient

@@ -71,6 +71,11 @@ typedef struct UmrRasterParams {
      * NULL / 0: nothing is saved (forward-only renders, generic modes). */
     void* pair_buffer;
     uint64_t pair_buffer_bytes;
+    /* 1: `textures` is ONE [F,T2,3] texture used by every image of the batch (a batch-shared parameter; the reference
+     * materialises `repeat(B,...)` copies, e.g. loss_utils.py:305) and `grad_textures` is the [F,T2,3] sum over the
+     * batch -- the images' gradients are accumulated directly, no [B,F,T2,3] intermediate.  0: per-image [B,F,T2,3]. */
+    int32_t shared_textures;
+    int32_t reserved_;
 } UmrRasterParams;
 
 const char* umr_error_string(int code);
@@ -178,6 +183,18 @@ int umr_masked_l1_backward(const float* pred, int64_t pred_bstride, const float*
                            int64_t mask_pred_bstride, const float* gt, const float* mask_gt,
                            const float* grad_loss, float* grad_pred, float* grad_mask_pred, int32_t B,
                            int32_t C, int64_t HW, void* stream);
+
+/* Fused loss head on one RGBA render: loss[0] = w_iou * mean_b neg_iou_loss(alpha, mask_gt) +
+ * w_tex * mean_b texture_loss_masks(rgb, gt, mask_gt, alpha) -- loss_utils.py:41-48 and :103-116 applied to the same
+ * render (the reference computes them with ~25 elementwise / reduce kernels; train_s1.py:211-215, bench step §8d).
+ * rgba [B,4,HW] (the renderer's output, contiguous), gt [B,3,HW], mask_gt [B,HW].
+ * stats [B,3] (written: I, U + 1e-6, sum|.|; needed by backward), per_image [B,2] = (1 - I/U, L1 mean), loss [1].
+ * Backward: grad_rgba [B,4,HW] fully written from the scalar grad_loss[1]. */
+int umr_loss_head_forward(const float* rgba, const float* gt, const float* mask_gt, float* stats, float* per_image,
+                          float* loss, int32_t B, int64_t HW, float w_iou, float w_tex, void* stream);
+int umr_loss_head_backward(const float* rgba, const float* gt, const float* mask_gt, const float* stats,
+                           const float* grad_loss, float* grad_rgba, int32_t B, int64_t HW, float w_iou, float w_tex,
+                           void* stream);
 
 /* distChamfer (chamfer_python.py:43-64) for D == 2 or 3.  a [B,N,D], b [B,M,D] ->
  * dist_ab[B,N], dist_ba[B,M], idx_ab[B,N] (int32), idx_ba[B,M] (int32), using the reference's

@@ -41,7 +41,7 @@ def test_scalar_entry_points_without_gpu():
 
 def test_params_struct_matches_header():
     p = _lib.UmrRasterParams()
-    assert ctypes.sizeof(p) == 5 * 4 + 6 * 4 + 5 * 4 + 3 * 4 + 4 + 2 * 8 + 8 + 8  # 4 bytes padding before the pointers
+    assert ctypes.sizeof(p) == 5 * 4 + 6 * 4 + 5 * 4 + 3 * 4 + 4 + 2 * 8 + 8 + 8 + 8  # 4 bytes padding before the pointers
     lib = _lib.load()
     assert lib.umr_sizeof_raster_params() == ctypes.sizeof(p)
     assert lib.umr_sizeof_project_params() == ctypes.sizeof(_lib.UmrProjectParams())

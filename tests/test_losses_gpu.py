@@ -152,3 +152,25 @@ def test_texture_loss_masks_fused(avg):
     (got * w.to(DEV)).sum().backward()
     _chk("masked l1", got, ref)
     _chk("masked l1 drgba", x.grad, r.grad, 1e-4, 1e-9)
+
+
+@pytest.mark.parametrize("B,H", [(3, 40), (16, 256), (2, 37)])
+def test_fused_loss_head_equals_the_two_reference_losses(B, H):
+    """loss_utils.mask_texture_loss == 2.5 * neg_iou_loss + 3.0 * texture_loss_masks (loss_utils.py:41-48, :103-116) on
+    the same RGBA render, value and gradient, against the torch-CPU oracle composition."""
+    g = torch.Generator().manual_seed(6)
+    rgba = torch.rand(B, 4, H, H, generator=g)
+    gt = torch.rand(B, 3, H, H, generator=g)
+    mgt = (torch.rand(B, H, H, generator=g) > 0.4).float()
+    r = rgba.clone().requires_grad_(True)
+    ref = 2.5 * oracle.neg_iou_loss(r[:, 3], mgt) + 3.0 * oracle.texture_loss_masks(r[:, :3], gt, mgt, r[:, 3])
+    (ref * 1.7).backward()
+    x = rgba.to(DEV).requires_grad_(True)
+    got = loss_utils.mask_texture_loss(x, gt.to(DEV), mgt.to(DEV), 2.5, 3.0)
+    (got * 1.7).backward()
+    _chk("loss head", got, ref, 1e-5, 1e-7)
+    _chk("loss head drgba", x.grad, r.grad, 1e-4, 1e-9)
+    # and the unfused product ops give the same number
+    y = rgba.to(DEV)
+    unfused = 2.5 * loss_utils.neg_iou_loss(y[:, 3], mgt.to(DEV)) + 3.0 * loss_utils.texture_loss_masks(y[:, :3], gt.to(DEV), mgt.to(DEV), y[:, 3])
+    _chk("fused vs unfused", got, unfused, 1e-5, 1e-7)

@@ -59,3 +59,33 @@ def test_forward_only_render_needs_no_pair_buffer():
     fv, tex = scene(1, 2, 1, seed=2)
     img, _, _ = raster.soft_rasterize(torch.from_numpy(fv).to(DEV), torch.from_numpy(tex).to(DEV), 32, anti_aliasing=True, **UMR)
     assert img.grad_fn is None
+
+
+@pytest.mark.parametrize("rgb", ["softmax", "hard"])
+@pytest.mark.parametrize("cand", [32.0, 0.0])
+def test_batch_shared_texture_equals_repeated_copies(rgb, cand):
+    """A [1,F,T2,3] texture is a batch-shared parameter (no repeat(B) copies, loss_utils.py:305): same images as the
+    materialised copies, and its gradient is the batch sum of the per-image gradients."""
+    B, IS = 3, 48
+    fv, tex = scene(B, 2, 3, seed=12)
+    tex1 = tex[:1]
+    g = np.random.default_rng(9).normal(size=(B, 4, IS, IS)).astype(np.float32)
+    old = raster.PAIR_CAND_PER_PIXEL
+    raster.PAIR_CAND_PER_PIXEL = cand
+    try:
+        outs = []
+        for shared in (True, False):
+            tfv = torch.from_numpy(fv).to(DEV).requires_grad_(True)
+            t = torch.from_numpy(tex1).to(DEV).requires_grad_(True)
+            tin = t if shared else t.expand(B, -1, -1, -1)
+            img, p2f, aggr = raster.soft_rasterize(tfv, tin, IS, aggr_func_rgb=rgb, anti_aliasing=True, **UMR)
+            img.backward(torch.from_numpy(g).to(DEV))
+            outs.append((img.detach().cpu().numpy(), tfv.grad.cpu().numpy(), t.grad.cpu().numpy()))
+    finally:
+        raster.PAIR_CAND_PER_PIXEL = old
+    assert np.array_equal(outs[0][0], outs[1][0])
+    ok, msg = rel_report("grad_faces", outs[0][1], outs[1][1], 1e-4, 1e-6 * float(np.abs(outs[1][1]).max()) + 1e-7)
+    assert ok, msg
+    assert outs[0][2].shape == (1,) + tex.shape[1:]
+    ok, msg = rel_report("grad_tex (batch sum)", outs[0][2], outs[1][2], 1e-4, 1e-6 * float(np.abs(outs[1][2]).max()) + 1e-7)
+    assert ok, msg

@@ -23,7 +23,8 @@ class UmrRasterParams(ctypes.Structure):
                 ("func_id_alpha", ctypes.c_int32), ("texture_sample_type", ctypes.c_int32),
                 ("double_side", ctypes.c_int32), ("background_color", ctypes.c_float * 3),
                 ("ev_kernel_start", ctypes.c_void_p), ("ev_kernel_stop", ctypes.c_void_p),
-                ("pair_buffer", ctypes.c_void_p), ("pair_buffer_bytes", ctypes.c_uint64)]
+                ("pair_buffer", ctypes.c_void_p), ("pair_buffer_bytes", ctypes.c_uint64),
+                ("shared_textures", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
 
 class UmrProjectParams(ctypes.Structure):
@@ -65,6 +66,10 @@ EXPORTS = {
     "umr_masked_l1_backward": (ctypes.c_int, [c_f32p, ctypes.c_int64, c_f32p, ctypes.c_int64, c_f32p, c_f32p, c_f32p,
                                               c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                               ctypes.c_void_p]),
+    "umr_loss_head_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                                     ctypes.c_void_p]),
+    "umr_loss_head_backward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+                                                      ctypes.c_void_p]),
     "umr_chamfer_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
     "umr_chamfer_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
     "umr_texcycle_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_int64,

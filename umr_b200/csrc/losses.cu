@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "umr_b200.h"
 
@@ -339,6 +341,90 @@ __global__ void __launch_bounds__(ML1_THREADS) k_masked_l1_bwd(const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused loss head:  w_iou * mean_b neg_iou(alpha, mask)  +  w_tex * mean_b masked_L1(rgb, gt, mask, alpha)
+// (loss_utils.py:41-48 and :103-116 evaluated on the SAME RGBA render, as train_s1.py:211-215 / the bench step do):
+// the RGBA image is read once, forward = one reduction + a one-warp finalize, backward = one kernel that writes the
+// complete [B,4,HW] image gradient (round 1: 2 + 2 kernels plus ~20 torch elementwise / fill / add launches).
+// ---------------------------------------------------------------------------------------------
+constexpr int LH_THREADS = 256;
+constexpr int LH_PER_CTA = LH_THREADS * 8;  // pixels per CTA
+
+// acc [B][3] += (sum alpha*m, sum alpha + m - alpha*m, sum_c |rgb_c*alpha - gt_c*m|)
+__global__ void __launch_bounds__(LH_THREADS) k_losshead_partial(const float* __restrict__ rgba, const float* __restrict__ gt,
+                                                                const float* __restrict__ mgt, float* __restrict__ acc,
+                                                                int64_t HW) {
+    const int b = blockIdx.y;
+    const float* im = rgba + (size_t)b * 4 * HW;
+    const float* g = gt + (size_t)b * 3 * HW;
+    const float* mg = mgt + (size_t)b * HW;
+    const int64_t begin = (int64_t)blockIdx.x * LH_PER_CTA;
+    const int64_t end = min(HW, begin + LH_PER_CTA);
+    float si = 0.f, su = 0.f, sl = 0.f;
+    for (int64_t i = begin + threadIdx.x; i < end; i += LH_THREADS) {
+        const float a = __ldg(im + 3 * HW + i), m = __ldg(mg + i);
+        si += a * m;
+        su += a + m - a * m;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sl += fabsf(__ldg(im + (size_t)c * HW + i) * a - __ldg(g + (size_t)c * HW + i) * m);
+    }
+    si = warp_sum(si); su = warp_sum(su); sl = warp_sum(sl);
+    __shared__ float s[3][LH_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s[0][warp] = si; s[1][warp] = su; s[2][warp] = sl; }
+    __syncthreads();
+    if (warp == 0) {
+        si = lane < LH_THREADS / 32 ? s[0][lane] : 0.f;
+        su = lane < LH_THREADS / 32 ? s[1][lane] : 0.f;
+        sl = lane < LH_THREADS / 32 ? s[2][lane] : 0.f;
+        si = warp_sum(si); su = warp_sum(su); sl = warp_sum(sl);
+        if (lane == 0) { atomicAdd(acc + b * 3 + 0, si); atomicAdd(acc + b * 3 + 1, su); atomicAdd(acc + b * 3 + 2, sl); }
+    }
+}
+// one warp: stats[b] = (I, U + 1e-6, per-image L1 mean); per_image[b] = (1 - I/U, L1 mean); loss = weighted batch means
+__global__ void k_losshead_finalize(float* __restrict__ acc, float* __restrict__ per_image, float* __restrict__ loss, int B,
+                                    float inv_n, float w_iou, float w_tex) {
+    float t_iou = 0.f, t_tex = 0.f;
+    for (int b = threadIdx.x; b < B; b += 32) {
+        const float I = acc[b * 3 + 0], U = acc[b * 3 + 1] + 1e-6f, L = acc[b * 3 + 2] * inv_n;
+        acc[b * 3 + 1] = U;
+        const float li = 1.f - I / U;
+        per_image[b * 2 + 0] = li;
+        per_image[b * 2 + 1] = L;
+        t_iou += li;
+        t_tex += L;
+    }
+    t_iou = warp_sum(t_iou); t_tex = warp_sum(t_tex);
+    if (threadIdx.x == 0) loss[0] = w_iou * (t_iou / B) + w_tex * (t_tex / B);
+}
+__global__ void __launch_bounds__(256) k_losshead_bwd(const float* __restrict__ rgba, const float* __restrict__ gt,
+                                                      const float* __restrict__ mgt, const float* __restrict__ acc,
+                                                      const float* __restrict__ gloss, float* __restrict__ grgba, int64_t HW,
+                                                      int B, float inv_n, float w_iou, float w_tex) {
+    const int b = blockIdx.y;
+    const float* im = rgba + (size_t)b * 4 * HW;
+    const float* g = gt + (size_t)b * 3 * HW;
+    const float* mg = mgt + (size_t)b * HW;
+    float* go = grgba + (size_t)b * 4 * HW;
+    const float gl = __ldg(gloss);
+    const float I = __ldg(acc + b * 3 + 0), U = __ldg(acc + b * 3 + 1);
+    const float ki = -(gl * w_iou / B) / (U * U);  // d(1 - I/U)/dalpha = -(m*U - I*(1-m)) / U^2
+    const float kt = gl * w_tex / B * inv_n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = __ldg(im + 3 * HW + i), m = __ldg(mg + i);
+        float ga = ki * (m * U - I * (1.f - m));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float pv = __ldg(im + (size_t)c * HW + i);
+            const float d = pv * a - __ldg(g + (size_t)c * HW + i) * m;
+            const float sg = d > 0.f ? kt : (d < 0.f ? -kt : 0.f);  // torch: grad * sign(d), sign(0) = 0
+            go[(size_t)c * HW + i] = sg * a;
+            ga += sg * pv;
+        }
+        go[3 * HW + i] = ga;
+    }
+}
+
 }  // namespace umr
 
 using namespace umr;
@@ -521,4 +607,31 @@ extern "C" int umr_masked_l1_backward(const float* pred, int64_t pred_bstride, c
     if (C == 3) k_masked_l1_bwd<3><<<grid, 256, 0, st>>>(pred, pred_bstride, mask_pred, mask_pred_bstride, gt, mask_gt, grad_loss, grad_pred, grad_mask_pred, HW, inv_n);
     else k_masked_l1_bwd<1><<<grid, 256, 0, st>>>(pred, pred_bstride, mask_pred, mask_pred_bstride, gt, mask_gt, grad_loss, grad_pred, grad_mask_pred, HW, inv_n);
     UMR_RET_LAST();
+}
+
+extern "C" int umr_loss_head_forward(const float* rgba, const float* gt, const float* mask_gt, float* stats,
+                                     float* per_image, float* loss, int32_t B, int64_t HW, float w_iou, float w_tex,
+                                     void* stream_) {
+    if (!rgba || !gt || !mask_gt || !stats || !per_image || !loss || B <= 0 || HW <= 0) return UMR_ERR_BAD_ARG;
+    if (B > 65535) return UMR_ERR_TOO_LARGE;
+    cudaStream_t st = (cudaStream_t)stream_;
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * 3 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    count_launch(2);
+    k_losshead_partial<<<dim3((unsigned)((HW + LH_PER_CTA - 1) / LH_PER_CTA), B), LH_THREADS, 0, st>>>(rgba, gt, mask_gt, stats, HW);
+    k_losshead_finalize<<<1, 32, 0, st>>>(stats, per_image, loss, B, 1.f / (3.f * (float)HW), w_iou, w_tex);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int umr_loss_head_backward(const float* rgba, const float* gt, const float* mask_gt, const float* stats,
+                                      const float* grad_loss, float* grad_rgba, int32_t B, int64_t HW, float w_iou,
+                                      float w_tex, void* stream_) {
+    if (!rgba || !gt || !mask_gt || !stats || !grad_loss || !grad_rgba || B <= 0 || HW <= 0) return UMR_ERR_BAD_ARG;
+    if (B > 65535) return UMR_ERR_TOO_LARGE;
+    cudaStream_t st = (cudaStream_t)stream_;
+    count_launch();
+    const unsigned gx = (unsigned)std::min<int64_t>((HW + 255) / 256, 1024);
+    k_losshead_bwd<<<dim3(gx, B), 256, 0, st>>>(rgba, gt, mask_gt, stats, grad_loss, grad_rgba, HW, B,
+                                                1.f / (3.f * (float)HW), w_iou, w_tex);
+    return (int)cudaGetLastError();
 }

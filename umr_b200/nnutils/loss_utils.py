@@ -65,6 +65,15 @@ def texture_loss_masks(img_pred, img_gt, mask_gt, mask_pred, avg=True):
     return torch.sum(loss, dim=(1, 2, 3)) / (loss.size(1) * loss.size(2) * loss.size(3))
 
 
+def mask_texture_loss(images, img_gt, mask_gt, mask_wt=1.0, tex_wt=1.0):
+    """Fused form of the two per-render losses the reference always applies to the SAME RGBA render
+    (train_s1.py:211-215; loss_utils.py:41-48 and :103-116):
+        mask_wt * neg_iou_loss(images[:, 3], mask_gt) + tex_wt * texture_loss_masks(images[:, :3], img_gt, mask_gt, images[:, 3])
+    One reduction kernel forward and one kernel backward (csrc/losses.cu `k_losshead_*`).  Not a reference name --
+    an addition; the two reference functions above stay available and give the same value."""
+    return ops.mask_texture_loss(images, img_gt, mask_gt, mask_wt, tex_wt)[0]
+
+
 def deform_l2reg(V):
     """loss_utils.py:118-123."""
     V = V.view(-1, V.size(2))

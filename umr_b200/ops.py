@@ -167,6 +167,56 @@ def masked_l1_per_image(img_pred, img_gt, mask_gt, mask_pred):
 
 
 # -------------------------------------------------------------------------------------------------
+# fused loss head: w_iou * neg_iou_loss(alpha, mask) + w_tex * texture_loss_masks(rgb, gt, mask, alpha)
+# -------------------------------------------------------------------------------------------------
+class LossHeadFunction(torch.autograd.Function):
+    """images [B,4,H,W] (one RGBA render), img_gt [B,3,H,W], mask_gt [B,H,W] -> (scalar loss, per_image [B,2]).
+    One reduction + finalize forward, ONE backward kernel writing the whole [B,4,H,W] image gradient."""
+
+    @staticmethod
+    def forward(ctx, images, img_gt, mask_gt, w_iou, w_tex):
+        _need_cuda(images, img_gt, mask_gt)
+        lib = _lib.load()
+        B, C, H, W = images.shape
+        if C != 4 or tuple(img_gt.shape) != (B, 3, H, W) or mask_gt.numel() != B * H * W:
+            raise ValueError("mask_texture_loss: images %s must be [B,4,H,W], img_gt %s [B,3,H,W], mask_gt %s [B,H,W]"
+                             % (tuple(images.shape), tuple(img_gt.shape), tuple(mask_gt.shape)))
+        x = images.detach().contiguous().float()
+        g = img_gt.detach().contiguous().float()
+        m = mask_gt.detach().contiguous().float()
+        with torch.cuda.device(x.device):
+            stats = torch.empty(B, 3, device=x.device, dtype=torch.float32)
+            per_image = torch.empty(B, 2, device=x.device, dtype=torch.float32)
+            loss = torch.empty((), device=x.device, dtype=torch.float32)
+            rc = lib.umr_loss_head_forward(_ptr(x), _ptr(g), _ptr(m), _ptr(stats), _ptr(per_image), _ptr(loss), B, H * W,
+                                           float(w_iou), float(w_tex), _stream_ptr(x.device))
+        _lib.check(rc, "umr_loss_head_forward")
+        ctx.save_for_backward(x, g, m, stats)
+        ctx.w = (float(w_iou), float(w_tex))
+        ctx.mark_non_differentiable(per_image)
+        return loss, per_image
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gp=None):
+        lib = _lib.load()
+        x, g, m, stats = ctx.saved_tensors
+        B, _, H, W = x.shape
+        gl = grad_loss.contiguous().float().reshape(1)
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x)
+            rc = lib.umr_loss_head_backward(_ptr(x), _ptr(g), _ptr(m), _ptr(stats), _ptr(gl), _ptr(gx), B, H * W,
+                                            ctx.w[0], ctx.w[1], _stream_ptr(x.device))
+        _lib.check(rc, "umr_loss_head_backward")
+        return gx, None, None, None, None
+
+
+def mask_texture_loss(images, img_gt, mask_gt, w_iou=1.0, w_tex=1.0):
+    """-> (loss, per_image[B,2] = (1 - IoU, masked L1)) with loss == w_iou * neg_iou_loss(images[:,3], mask_gt) +
+    w_tex * texture_loss_masks(images[:,:3], img_gt, mask_gt, images[:,3])."""
+    return LossHeadFunction.apply(images, img_gt, mask_gt, w_iou, w_tex)
+
+
+# -------------------------------------------------------------------------------------------------
 # chamfer
 # -------------------------------------------------------------------------------------------------
 class ChamferFunction(torch.autograd.Function):
