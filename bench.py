@@ -204,7 +204,9 @@ class Workload:
             self.dev.append([t.to(device) for t in h])
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
         from umr_b200.dist import FlatGradAllReduce
-        self.reducer = FlatGradAllReduce([self.mean_shape, self.texture], average=True)
+        self.reducer = FlatGradAllReduce([self.mean_shape, self.texture], average=True,
+                                         backend=os.environ.get("UMR_ALLREDUCE", "auto"))
+        self.reduce_in_graph = self.reducer.backend in ("p2p", "none")
         self.stage = [torch.empty_like(t, device=device) for t in self.host[0]]
         self.stage2 = None
 
@@ -212,9 +214,7 @@ class Workload:
         import torch
         from umr_b200.nnutils import loss_utils
         delta, cams, imgs, masks = inputs
-        B = delta.shape[0]
-        self.mean_shape.grad = None
-        self.texture.grad = None
+        self.reducer.zero_grads()         # .grad of the shared parameters are views of ONE flat buffer (no pack/unpack)
         verts = self.mean_shape[None] + delta
         tex = self.texture[None]          # [1,F,T2,3]: batch-shared texture parameter (no repeat(B) copies)
         images, _, _ = self.renderer(verts, self.faces, cams, tex)
@@ -222,16 +222,16 @@ class Workload:
         # fused: one reduction forward, one kernel backward (tests/test_losses_gpu.py checks it against the composition)
         loss = loss_utils.mask_texture_loss(images, imgs, masks, 2.5, 3.0)
         loss.backward()
-        if reduce:
-            self.reducer()  # N>1: ONE NCCL all-reduce of the flat [V*3 + F*T2*3] gradient
-        else:
-            self.reducer.pack()  # (graph mode: the collective itself is issued outside the captured graph)
+        # N>1: ONE all-reduce of the flat [V*3 + F*T2*3] gradient.  Our p2p kernel is a plain kernel and
+        # lives inside the captured graph; an NCCL fallback is issued after the replay (finish()).
+        if reduce or self.reduce_in_graph:
+            self.reducer.reduce()
         return loss
 
     def finish(self):
-        """The part of a step that stays outside the CUDA graph: the NCCL all-reduce + scatter back."""
-        self.reducer.reduce()
-        self.reducer.unpack()
+        """The part of a step that stays outside the CUDA graph: only the NCCL fallback of the all-reduce."""
+        if not self.reduce_in_graph:
+            self.reducer.reduce()
 
     def step_resident(self, i, world):
         return self.step(self.dev[i % NUM_SETS], world)
@@ -411,7 +411,10 @@ def run_gpu(args, cfg):
                    "vertices": wl.V, "texture_res": cfg["tex_res"], "parallelism": "dp%d" % world,
                    "l2": "inputs rotate over %d pre-generated batches (> 126 MB L2 together with the per-step "
                          "buffers)" % NUM_SETS,
-                   "cuda_graph": use_graph, "eager_ms_per_step": ms_eager / K},
+                   "cuda_graph": use_graph, "eager_ms_per_step": ms_eager / K,
+                   "allreduce": {"none": "single process", "p2p": "own one-shot kernel over NVLink peer memory "
+                                 "(umr_p2p_allreduce), inside the captured graph", "nccl": "ncclAllReduce(AVG) issued after "
+                                 "each graph replay"}.get(wl.reducer.backend, wl.reducer.backend)},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K,
                 "pipeline": "H2D of step i+1 (copy stream, pinned memory) overlaps the graph replay of step i; "

@@ -219,6 +219,20 @@ int umr_texcycle_backward(const float* flow, const float* prob, const uint8_t* v
                           const float* grad_loss, float* grad_flow, int32_t B, int32_t F,
                           int32_t T2, void* stream);
 
+/* One-shot all-reduce of the flat shared-parameter gradient over NVLink peer memory (reference:
+ * the implicit gradient reduce of torch.nn.DataParallel, experiments/train_s2.py:101,133,149,164).
+ *   peer_buffers_dev  device array of `world` uint64: the address of every rank's SYMMETRIC buffer as mapped into this
+ *                     process (rank r's own buffer at index r).  Each buffer holds n_floats fp32 gradient values and,
+ *                     at flag_offset_bytes (16-byte aligned, >= 4*n_floats), umr_p2p_allreduce_flag_bytes() bytes of flag
+ *                     words, zero-initialised ONCE by the caller before the first call.
+ *   out               local [n_floats]: scale * sum over ranks (every rank computes the same bits).
+ *   local_state       16 bytes of local device memory, zero-initialised once.
+ * n_floats must be a multiple of 4.  Every rank must issue the same sequence of calls.  The call only enqueues one
+ * kernel (CUDA-graph capturable); when it has completed, the symmetric buffer may be overwritten. */
+size_t umr_p2p_allreduce_flag_bytes(void);
+int umr_p2p_allreduce(const void* peer_buffers_dev, float* out, int64_t n_floats, int64_t flag_offset_bytes,
+                      void* local_state, int32_t rank, int32_t world, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

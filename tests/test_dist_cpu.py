@@ -27,10 +27,21 @@ def _worker(rank, world, port, ret):
     lo, hi = shard_range(6, rank, world)
     _loss(shape, tex, delta[lo:hi], target[lo:hi]).backward()
     red = FlatGradAllReduce([shape, tex], average=False)
-    flat = red()
+    assert red.backend == "gloo"
+    flat = red()                      # round-1 interface: pack -> all-reduce -> unpack
     if rank == 0:
         ret["flat"] = flat.clone()
         ret["g_shape"] = shape.grad.clone()
+    # round-2 interface: .grad are views of the flat buffer, autograd accumulates into it, no pack / unpack
+    red2 = FlatGradAllReduce([shape, tex], average=True)
+    for _ in range(2):                # second pass: zero_grads() really restarts the accumulation
+        red2.zero_grads()
+        assert shape.grad.data_ptr() == red2.flat.data_ptr()
+        _loss(shape, tex, delta[lo:hi], target[lo:hi]).backward()
+        out = red2.reduce()
+    if rank == 0:
+        ret["avg"] = out[:red2.n].clone()
+        ret["g_tex_avg"] = tex.grad.clone()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -49,6 +60,8 @@ def test_sharded_gradient_equals_full_batch_gradient():
     full = torch.cat([shape.grad.reshape(-1), tex.grad.reshape(-1)])
     assert torch.allclose(ret["flat"], full, rtol=1e-5, atol=1e-6)
     assert torch.allclose(ret["g_shape"], shape.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ret["avg"], full / world, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ret["g_tex_avg"], tex.grad / world, rtol=1e-5, atol=1e-6)
 
 
 def test_single_process_is_identity():
@@ -56,3 +69,9 @@ def test_single_process_is_identity():
     (p * torch.arange(4.)).sum().backward()
     FlatGradAllReduce([p])()
     assert torch.equal(p.grad, torch.arange(4.))
+    red = FlatGradAllReduce([p])
+    assert red.backend == "none"
+    red.zero_grads()
+    (p * torch.arange(4.)).sum().backward()
+    red.reduce()
+    assert torch.equal(p.grad, torch.arange(4.)) and p.grad.data_ptr() == red.flat.data_ptr()

@@ -70,6 +70,9 @@ EXPORTS = {
                                                      ctypes.c_void_p]),
     "umr_loss_head_backward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_void_p]),
+    "umr_p2p_allreduce_flag_bytes": (ctypes.c_size_t, []),
+    "umr_p2p_allreduce": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
+                                         ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]),
     "umr_chamfer_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
     "umr_chamfer_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
     "umr_texcycle_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_int64,
