@@ -80,9 +80,16 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(const uint64_t* __restric
     // ---- 2. sum the peers' buffers ---------------------------------------------------------------------------
     for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; ++r) {  // same order on every rank: bit-identical results everywhere
-            const float4 v = ld_peer_f4(reinterpret_cast<const float4*>(peer_bufs[r]) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        // all peer loads of a batch are issued before the first one is consumed (one NVLink round trip per batch of 8
+        // ranks instead of one per rank); summed in rank order on every rank: bit-identical results everywhere
+        for (int r0 = 0; r0 < world; r0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (r0 + q < world) v[q] = ld_peer_f4(reinterpret_cast<const float4*>(peer_bufs[r0 + q]) + i);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (r0 + q < world) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
         }
         reinterpret_cast<float4*>(out)[i] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
     }

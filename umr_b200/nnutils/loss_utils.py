@@ -179,10 +179,19 @@ class CorrLossChamfer(nn.Module):
         nums.append(nums[2] + self.back_num)
         self.nums = nums
 
+    def _index_on(self, device):
+        """Concatenated part-vertex indices on `device`, uploaded once (the reference indexes with CPU tensors on every
+        call, loss_utils.py:227-230 -- an H2D copy per step that also breaks CUDA-graph capture)."""
+        cache = self.__dict__.setdefault("_idx_cache", {})
+        key = str(device)
+        if key not in cache:
+            cache[key] = torch.cat((self.head_vertices, self.belly_vertices, self.neck_vertices, self.back_vertices)).to(device)
+        return cache[key]
+
     def forward(self, head_points, belly_points, neck_points, back_points, verts, cams, avg=True):
         groups = (self.head_vertices, self.belly_vertices, self.neck_vertices, self.back_vertices)
         targets = (head_points, belly_points, neck_points, back_points)
-        idx = torch.cat(groups).to(verts.device)
+        idx = self._index_on(verts.device)
         vert2d = self.renderer.project_points(verts[:, idx, :], cams)  # [B, sum(sizes), 2]
         terms, start = [], 0
         for group, target, weight in zip(groups, targets, self.weights):
