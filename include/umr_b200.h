@@ -219,6 +219,38 @@ int umr_texcycle_backward(const float* flow, const float* prob, const uint8_t* v
                           const float* grad_loss, float* grad_flow, int32_t B, int32_t F,
                           int32_t T2, void* stream);
 
+/* Texture atlas (SoftRas natives).
+ * umr_create_texture_image: cuda/create_texture_image_cuda_kernel.cu:10-105.  faces_uv [F,3,2] (pixel coordinates of the
+ *   three corners in the atlas), textures [F,R*R,3] -> image [H,W,3] (pixels of tiles >= F are left untouched).
+ * umr_load_textures: cuda/load_textures_cuda_kernel.cu:8-98.  image [H,W,3], faces_uv [F,3,2] in [0,1], is_update [F]
+ *   int32 -> textures [F,R*R,3] (faces with is_update == 0 are left untouched); bilinear. */
+int umr_create_texture_image(const float* faces_uv, const float* textures, float* image, int32_t num_faces,
+                             int32_t texture_res_in, int32_t image_height, int32_t image_width, float eps, void* stream);
+int umr_load_textures(const float* image, const float* faces_uv, const int32_t* is_update, float* textures,
+                      int32_t num_faces, int32_t texture_res, int32_t image_height, int32_t image_width, void* stream);
+
+/* Mesh regularisers (SoftRas/losses.py).
+ * Laplacian (losses.py:6-37): CSR neighbour table rowptr [V+1], col [nnz], coef [nnz] (off-diagonal entries of the
+ *   row-normalised Laplacian; the diagonal is 1); x [B,V,3] -> y [B,V,3] = L x (saved for backward), loss [B] = |y|^2.
+ *   Backward: tcoef [nnz] = coef of row col[e] towards the row's vertex (the transposed entries); grad_x [B,V,3].
+ * Flatten (losses.py:39-114): edges [E,4] = (v0, v1, v2, v3) int32; loss [B] = sum_e (cos + 1)^2; backward zero-fills
+ *   grad_vertices [B,V,3] and accumulates. */
+int umr_laplacian_forward(const float* x, const int32_t* rowptr, const int32_t* col, const float* coef, float* y,
+                          float* loss, int32_t B, int32_t V, void* stream);
+int umr_laplacian_backward(const float* y, const int32_t* rowptr, const int32_t* col, const float* tcoef,
+                           const float* grad_loss, float* grad_x, int32_t B, int32_t V, void* stream);
+int umr_flatten_forward(const float* vertices, const int32_t* edges, float* loss, int32_t B, int32_t V, int32_t E,
+                        float eps, void* stream);
+int umr_flatten_backward(const float* vertices, const int32_t* edges, const float* grad_loss, float* grad_vertices,
+                         int32_t B, int32_t V, int32_t E, float eps, void* stream);
+
+/* Barrier distance transform of the GT masks (utils/image.py:130-141 `compute_dt_barrier`, run with scipy on the host
+ * per image per step at train_s2.py:196): mask [B,H,W] (non-zero = object) -> dt [B,H,W] =
+ * 1 / (1 + exp(-k * (EDT(1-mask) - EDT(mask)) / max(H,W))), exact Euclidean distances.  workspace:
+ * umr_dt_barrier_workspace_bytes(B,H,W) bytes of device scratch. */
+size_t umr_dt_barrier_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int umr_dt_barrier(const float* mask, float* dt, void* workspace, int32_t B, int32_t H, int32_t W, float k, void* stream);
+
 /* One-shot all-reduce of the flat shared-parameter gradient over NVLink peer memory (reference:
  * the implicit gradient reduce of torch.nn.DataParallel, experiments/train_s2.py:101,133,149,164).
  *   peer_buffers_dev  device array of `world` uint64: the address of every rank's SYMMETRIC buffer as mapped into this

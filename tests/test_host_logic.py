@@ -306,3 +306,25 @@ def test_corr_loss_chamfer_matches_reference_expression(monkeypatch):
     assert torch.allclose(vert2d, v2d, atol=1e-6) and torch.allclose(loss, ref, atol=1e-6)
     per_sample = m(pts[0], pts[1], pts[2], pts[3], verts, cams, avg=False)
     assert per_sample.shape == (B,)
+
+
+def test_regulariser_cpu_formulas_match_the_reference_restatement():
+    """soft_renderer.LaplacianLoss / FlattenLoss (CPU branch, and the CSR table the CUDA kernels use) vs oracle/mesh_oracle.py."""
+    import mesh_oracle as MO
+    v, f = synth.icosphere(2)
+    verts = torch.from_numpy(synth.bird_like(v, np.random.default_rng(0), 2))
+    faces = torch.from_numpy(f.astype(np.int64))
+    lap = sr.LaplacianLoss(torch.from_numpy(v), faces)
+    assert torch.allclose(lap(verts), MO.laplacian_loss(verts, f), rtol=1e-5)
+    assert torch.allclose(sr.FlattenLoss(faces)(verts), MO.flatten_loss(verts, f), rtol=1e-5)
+    # CSR == off-diagonal part of the dense matrix; tcoef == transposed entries
+    dense = MO.laplacian_matrix(v.shape[0], f)
+    rp, col, coef, tcoef = lap.csr_rowptr.numpy(), lap.csr_col.numpy(), lap.csr_coef.numpy(), lap.csr_tcoef.numpy()
+    rec = torch.eye(v.shape[0])
+    for i in range(v.shape[0]):
+        for e in range(rp[i], rp[i + 1]):
+            rec[i, col[e]] = float(coef[e])
+            assert float(tcoef[e]) == float(dense[col[e], i])
+    assert torch.equal(rec, dense)
+    ft = sr.FlattenLoss(faces).edge_table
+    assert ft.shape[1] == 4 and ft.dtype == torch.int32 and ft.shape[0] == 3 * f.shape[0] // 2

@@ -70,6 +70,14 @@ EXPORTS = {
                                                      ctypes.c_void_p]),
     "umr_loss_head_backward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_void_p]),
+    "umr_create_texture_image": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 4 + [ctypes.c_float, ctypes.c_void_p]),
+    "umr_load_textures": (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int32] * 4 + [ctypes.c_void_p]),
+    "umr_laplacian_forward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32] * 2 + [ctypes.c_void_p]),
+    "umr_laplacian_backward": (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int32] * 2 + [ctypes.c_void_p]),
+    "umr_flatten_forward": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 3 + [ctypes.c_float, ctypes.c_void_p]),
+    "umr_flatten_backward": (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int32] * 3 + [ctypes.c_float, ctypes.c_void_p]),
+    "umr_dt_barrier_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 3),
+    "umr_dt_barrier": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 3 + [ctypes.c_float, ctypes.c_void_p]),
     "umr_p2p_allreduce_flag_bytes": (ctypes.c_size_t, []),
     "umr_p2p_allreduce": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
                                          ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]),

@@ -301,3 +301,121 @@ class TexCycleFunction(torch.autograd.Function):
 
 def tex_cycle(flow, prob, face_ids):
     return TexCycleFunction.apply(flow, prob, face_ids)
+
+
+# -------------------------------------------------------------------------------------------------
+# mesh regularisers (SoftRas/losses.py) and the barrier distance transform (utils/image.py)
+# -------------------------------------------------------------------------------------------------
+class LaplacianFunction(torch.autograd.Function):
+    """x [B,V,3] + CSR neighbour table -> per-sample |L x|^2 [B] (SoftRas/losses.py:31-37)."""
+
+    @staticmethod
+    def forward(ctx, x, rowptr, col, coef, tcoef):
+        _need_cuda(x)
+        lib = _lib.load()
+        xx = x.detach().contiguous().float()
+        B, V = xx.shape[:2]
+        with torch.cuda.device(xx.device):
+            y = torch.empty_like(xx)
+            loss = torch.empty(B, device=xx.device, dtype=torch.float32)
+            rc = lib.umr_laplacian_forward(_ptr(xx), _ptr(rowptr), _ptr(col), _ptr(coef), _ptr(y), _ptr(loss), B, V,
+                                           _stream_ptr(xx.device))
+        _lib.check(rc, "umr_laplacian_forward")
+        ctx.save_for_backward(y, rowptr, col, tcoef)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        y, rowptr, col, tcoef = ctx.saved_tensors
+        B, V = y.shape[:2]
+        gl = g.contiguous().float()
+        with torch.cuda.device(y.device):
+            gx = torch.empty_like(y)
+            rc = lib.umr_laplacian_backward(_ptr(y), _ptr(rowptr), _ptr(col), _ptr(tcoef), _ptr(gl), _ptr(gx), B, V,
+                                            _stream_ptr(y.device))
+        _lib.check(rc, "umr_laplacian_backward")
+        return gx, None, None, None, None
+
+
+class FlattenFunction(torch.autograd.Function):
+    """vertices [B,V,3] + edge table [E,4] int32 -> per-sample sum_e (cos + 1)^2 [B] (SoftRas/losses.py:71-114)."""
+
+    @staticmethod
+    def forward(ctx, vertices, edges, eps):
+        _need_cuda(vertices)
+        lib = _lib.load()
+        v = vertices.detach().contiguous().float()
+        B, V = v.shape[:2]
+        E = edges.shape[0]
+        with torch.cuda.device(v.device):
+            loss = torch.empty(B, device=v.device, dtype=torch.float32)
+            rc = lib.umr_flatten_forward(_ptr(v), _ptr(edges), _ptr(loss), B, V, E, float(eps), _stream_ptr(v.device))
+        _lib.check(rc, "umr_flatten_forward")
+        ctx.save_for_backward(v, edges)
+        ctx.eps = float(eps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        v, edges = ctx.saved_tensors
+        B, V = v.shape[:2]
+        gl = g.contiguous().float()
+        with torch.cuda.device(v.device):
+            gv = torch.empty_like(v)
+            rc = lib.umr_flatten_backward(_ptr(v), _ptr(edges), _ptr(gl), _ptr(gv), B, V, edges.shape[0], ctx.eps,
+                                          _stream_ptr(v.device))
+        _lib.check(rc, "umr_flatten_backward")
+        return gv, None, None
+
+
+def dt_barrier(masks, k=50.0):
+    """utils/image.py:130-141 `compute_dt_barrier` for a batch on the GPU: masks [B,H,W] or [H,W] (non-zero = object)
+    -> same shape float32, exact Euclidean distances (the reference runs scipy on the host per image per step)."""
+    _need_cuda(masks)
+    lib = _lib.load()
+    m = masks.detach().float()
+    squeeze = m.dim() == 2
+    if squeeze:
+        m = m[None]
+    m = m.contiguous()
+    B, H, W = m.shape
+    with torch.cuda.device(m.device):
+        out = torch.empty_like(m)
+        ws = torch.empty(lib.umr_dt_barrier_workspace_bytes(B, H, W), device=m.device, dtype=torch.uint8)
+        rc = lib.umr_dt_barrier(_ptr(m), _ptr(out), _ptr(ws), B, H, W, float(k), _stream_ptr(m.device))
+    _lib.check(rc, "umr_dt_barrier")
+    return out[0] if squeeze else out
+
+
+def create_texture_image(faces_uv, textures, image, eps=1e-5):
+    """SoftRas cuda/create_texture_image (in place on `image` [H,W,3]); faces_uv [F,3,2], textures [F,R*R,3]."""
+    _need_cuda(faces_uv, textures, image)
+    lib = _lib.load()
+    f = faces_uv.contiguous().float()
+    t = textures.contiguous().float()
+    if not image.is_contiguous() or image.dtype != torch.float32:
+        raise ValueError("image must be a contiguous float32 [H,W,3] tensor")
+    F_ = t.shape[0]
+    R = int(round(t.shape[1] ** 0.5))
+    rc = lib.umr_create_texture_image(_ptr(f), _ptr(t), _ptr(image), F_, R, image.shape[0], image.shape[1], float(eps),
+                                      _stream_ptr(image.device))
+    _lib.check(rc, "umr_create_texture_image")
+    return image
+
+
+def load_textures(image, faces_uv, textures, is_update):
+    """SoftRas cuda/load_textures (in place on `textures` [F,R*R,3]); image [H,W,3], faces_uv [F,3,2], is_update [F] int32."""
+    _need_cuda(image, faces_uv, textures, is_update)
+    lib = _lib.load()
+    img = image.contiguous().float()
+    f = faces_uv.contiguous().float()
+    u = is_update.contiguous().int()
+    if not textures.is_contiguous() or textures.dtype != torch.float32:
+        raise ValueError("textures must be a contiguous float32 [F,R*R,3] tensor")
+    R = int(round(textures.shape[1] ** 0.5))
+    rc = lib.umr_load_textures(_ptr(img), _ptr(f), _ptr(u), _ptr(textures), textures.shape[0], R, img.shape[0], img.shape[1],
+                               _stream_ptr(textures.device))
+    _lib.check(rc, "umr_load_textures")
+    return textures

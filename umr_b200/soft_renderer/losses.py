@@ -1,5 +1,7 @@
-"""Mesh regularisers UMR takes from SoftRas (reference: SoftRas/losses.py:6-114;
-call sites experiments/train_s2.py:138-139).  Pure torch -- tiny per-step costs."""
+"""Mesh regularisers UMR takes from SoftRas (reference: SoftRas/losses.py:6-114; call sites
+experiments/train_s2.py:138-139, :220-221).  CUDA inputs run hand-written kernels (csrc/mesh_ops.cu):
+the Laplacian is a CSR neighbour gather instead of the reference's dense V x V matmul, the flatten loss one fused
+kernel per direction instead of ~40 elementwise launches.  CPU inputs evaluate the reference's formulas in torch."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -22,9 +24,23 @@ class LaplacianLoss(nn.Module):
         lap[idx, idx] = -lap.sum(1)
         lap = lap / lap[idx, idx][:, None]
         self.register_buffer("laplacian", torch.from_numpy(lap))
+        # CSR of the off-diagonal entries (values exactly as in the dense matrix) + the transposed entries for backward
+        off = lap.copy()
+        off[idx, idx] = 0
+        rows, cols = np.nonzero(off)
+        rowptr = np.zeros(self.nv + 1, np.int32)
+        np.add.at(rowptr, rows + 1, 1)
+        self.register_buffer("csr_rowptr", torch.from_numpy(np.cumsum(rowptr).astype(np.int32)))
+        self.register_buffer("csr_col", torch.from_numpy(cols.astype(np.int32)))
+        self.register_buffer("csr_coef", torch.from_numpy(off[rows, cols].astype(np.float32)))
+        self.register_buffer("csr_tcoef", torch.from_numpy(off[cols, rows].astype(np.float32)))
 
     def forward(self, x):
         batch_size = x.size(0)
+        if x.is_cuda and x.dim() == 3 and x.size(-1) == 3:
+            from .. import ops
+            loss = ops.LaplacianFunction.apply(x, self.csr_rowptr, self.csr_col, self.csr_coef, self.csr_tcoef)
+            return loss.sum() / batch_size if self.average else loss
         x = torch.matmul(self.laplacian, x)
         x = x.pow(2).sum(tuple(range(1, x.dim())))
         return x.sum() / batch_size if self.average else x
@@ -52,6 +68,7 @@ class FlattenLoss(nn.Module):
         v3 = [opp[e][1] for e in edges]
         for name, v in (("v0s", v0), ("v1s", v1), ("v2s", v2), ("v3s", v3)):
             self.register_buffer(name, torch.tensor(v, dtype=torch.long))
+        self.register_buffer("edge_table", torch.tensor(list(zip(v0, v1, v2, v3)), dtype=torch.int32).reshape(-1, 4))
 
     @staticmethod
     def _perp(a, b, eps):
@@ -68,6 +85,10 @@ class FlattenLoss(nn.Module):
 
     def forward(self, vertices, eps=1e-6):
         batch_size = vertices.size(0)
+        if vertices.is_cuda and vertices.dim() == 3:
+            from .. import ops
+            loss = ops.FlattenFunction.apply(vertices, self.edge_table, eps)
+            return loss.sum() / batch_size if self.average else loss
         p0, p1 = vertices[:, self.v0s, :], vertices[:, self.v1s, :]
         p2, p3 = vertices[:, self.v2s, :], vertices[:, self.v3s, :]
         cb1, l1 = self._perp(p1 - p0, p2 - p0, eps)

@@ -2,9 +2,11 @@
 
 Holds vertices [B,V,3], faces [B,F,3] (int) and textures (surface: [B,F,T2,3]; vertex: [B,V,3]).  Derived
 quantities (`face_vertices`, `surface_normals`, `vertex_normals`) are cached until vertices or faces are
-reassigned.  OBJ loading / saving are host-side I/O outside the hot path: `save_obj` writes geometry only.
+reassigned.  OBJ loading / saving (incl. the texture atlas kernels) live in functional/obj_io.py.
 """
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -127,14 +129,16 @@ class Mesh(object):
 
     # --- host I/O (outside the hot path) ----------------------------------------------------
     def save_obj(self, filename_obj, save_texture=False, texture_res_out=16):
+        """SoftRas/mesh.py:141-148: geometry, plus (save_texture) the texture atlas PNG / .mtl written from the
+        `create_texture_image` kernel (csrc/mesh_ops.cu)."""
         if self.batch_size != 1:
             raise ValueError("Could not save when batch size >= 1")
-        v = self._vertices[0].detach().cpu().numpy()
-        f = self._faces[0].detach().cpu().numpy()
-        with open(filename_obj, "w") as fh:
-            fh.write("# umr_b200 soft_renderer.Mesh.save_obj (geometry only)\n")
-            fh.writelines("v %.8f %.8f %.8f\n" % tuple(p) for p in v)
-            fh.writelines("f %d %d %d\n" % tuple(t + 1) for t in f)
+        from .functional.obj_io import save_obj
+        if save_texture:
+            save_obj(filename_obj, self._vertices[0], self._faces[0], textures=self._textures[0],
+                     texture_res=texture_res_out, texture_type=self.texture_type)
+        else:
+            save_obj(filename_obj, self._vertices[0], self._faces[0], textures=None)
 
     @classmethod
     def from_obj(cls, filename_obj, normalization=False, load_texture=False, texture_res=1, texture_type="surface"):
@@ -156,4 +160,16 @@ class Mesh(object):
             v = v / torch.abs(v).max()
             v = v * 2
             v = v - v.max(0)[0][None, :] / 2
-        return cls(v, f, None, texture_res, texture_type)
+        textures = None
+        if load_texture and texture_type == "surface":  # functional/load_obj.py:139-146
+            from .functional.obj_io import load_textures
+            with open(filename_obj) as fh:
+                mtl = [ln.split()[1] for ln in fh if ln.startswith("mtllib")]
+            if not mtl:
+                raise Exception("Failed to load textures.")
+            textures = load_textures(filename_obj, os.path.join(os.path.dirname(filename_obj), mtl[-1]), texture_res)
+        elif load_texture and texture_type == "vertex":  # :147-154: colours ride on the `v` lines
+            with open(filename_obj) as fh:
+                cols = [[float(x) for x in ln.split()[4:7]] for ln in fh if ln.split() and ln.split()[0] == "v"]
+            textures = torch.tensor(cols, dtype=torch.float32).cuda()
+        return cls(v, f, textures, texture_res, texture_type)
