@@ -71,9 +71,9 @@ typedef struct UmrRasterParams {
      * NULL / 0: nothing is saved (forward-only renders, generic modes). */
     void* pair_buffer;
     uint64_t pair_buffer_bytes;
-    /* 1: `textures` is ONE [F,T2,3] texture used by every image of the batch (a batch-shared parameter; the reference
-     * materialises `repeat(B,...)` copies, e.g. loss_utils.py:305) and `grad_textures` is the [F,T2,3] sum over the
-     * batch -- the images' gradients are accumulated directly, no [B,F,T2,3] intermediate.  0: per-image [B,F,T2,3]. */
+    /* Texture sharing: G = shared_textures consecutive images use ONE [F,T2,3] texture -- `textures` (and `grad_textures`,
+     * summed over each group) are [B/G,F,T2,3].  G == B: one batch-shared parameter; G == 8: the camera hypotheses of a
+     * sample (the reference materialises repeat(...) copies, loss_utils.py:305: 70.8 MB at batch 16).  0 or 1: per-image. */
     int32_t shared_textures;
     int32_t reserved_;
 } UmrRasterParams;
@@ -135,6 +135,10 @@ typedef struct UmrProjectParams {
     int32_t light_enabled;       /* 0: `light` is not written */
     float light_intensity_ambient, light_intensity_directional;
     float light_color_ambient[3], light_color_directional[3], light_direction[3];
+    /* > 1: every `num_hypotheses` consecutive renders (camera hypotheses, cams [B,7]) share ONE mesh: vertices are
+     * [B / num_hypotheses, V, 3] (faces likewise when batched) -- the reference materialises repeat(1, 8, ...) copies
+     * (loss_utils.py:260-261, 303-304); grad_vertices is [B / num_hypotheses, V, 3], summed over the hypotheses. */
+    int32_t num_hypotheses;
 } UmrProjectParams;
 
 /* vertices [B,V,3] f32, cams [B,7] = [s,tx,ty,qw,qx,qy,qz], faces int32 -> face_vertices [B,F,9]

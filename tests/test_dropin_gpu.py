@@ -188,3 +188,43 @@ def test_part_matching_loss_packed_renders_match_reference_pattern():
     assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * max(1.0, abs(outs[1][0]))
     ok, msg = rel_report("dverts", outs[0][2].numpy(), outs[1][2].numpy(), 1e-3, 1e-5 * float(outs[1][2].abs().max()))
     assert ok, msg
+
+
+def test_camera_hypotheses_are_broadcast_not_materialised():
+    """SoftRenderer.forward(vs [B], fs [B], cams [B*H], tx [B]) == the reference's call with
+    repeat(1, H, ...) copies (loss_utils.py:260-261, 303-305): same images, gradients summed over the hypotheses,
+    and no [B*H,F,T2,3] texture tensor is ever allocated."""
+    B, H, IS, T = 2, 8, 32, 6
+    rng = np.random.default_rng(3)
+    v, f = synth.icosphere(2)
+    F_ = f.shape[0]
+    vs0 = torch.from_numpy(synth.bird_like(v, rng, B))
+    fs = torch.from_numpy(f.astype(np.int64))[None].repeat(B, 1, 1).to(DEV)
+    cams = torch.from_numpy(np.stack([synth.cameras(rng, H) for _ in range(B)])).view(-1, 7).to(DEV)
+    tx0 = torch.from_numpy(rng.uniform(0, 1, size=(B, F_, T * T, 3)).astype(np.float32))
+    w = torch.linspace(0.5, 1.5, B * H * 4 * IS * IS, device=DEV).view(B * H, 4, IS, IS)
+    outs, peaks = [], []
+    for tiled in (False, True):
+        r = smr.SoftRenderer(IS, "softmax")
+        r.ambient_light_only()
+        vs = vs0.clone().to(DEV).requires_grad_(True)
+        tx = tx0.clone().to(DEV).requires_grad_(True)
+        c = cams.clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        if tiled:
+            img, _, _ = r(loss_utils.tile_hypotheses(vs, H), loss_utils.tile_hypotheses(fs, H), c, loss_utils.tile_hypotheses(tx, H))
+        else:
+            img, _, _ = r(vs, fs, c, tx)
+        peaks.append(torch.cuda.max_memory_allocated() - base)
+        (img * w).sum().backward()
+        outs.append((img.detach().cpu().numpy(), vs.grad.cpu().numpy(), tx.grad.cpu().numpy(), c.grad.cpu().numpy()))
+    a, b = outs
+    assert np.array_equal(a[0], b[0]), "broadcast render differs from the materialised one"
+    for k, name in ((1, "dverts"), (2, "dtex"), (3, "dcams")):
+        ok, msg = rel_report(name, a[k], b[k], 2e-4, 2e-5 * float(np.abs(b[k]).max()))
+        print(msg)
+        assert ok, msg
+    tiled_tex_bytes = B * H * F_ * T * T * 3 * 4
+    assert peaks[1] - peaks[0] >= 0.9 * tiled_tex_bytes, (peaks, tiled_tex_bytes)

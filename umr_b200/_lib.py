@@ -34,7 +34,7 @@ class UmrProjectParams(ctypes.Structure):
                 ("light_enabled", ctypes.c_int32),
                 ("light_intensity_ambient", ctypes.c_float), ("light_intensity_directional", ctypes.c_float),
                 ("light_color_ambient", ctypes.c_float * 3), ("light_color_directional", ctypes.c_float * 3),
-                ("light_direction", ctypes.c_float * 3)]
+                ("light_direction", ctypes.c_float * 3), ("num_hypotheses", ctypes.c_int32)]
 
 
 EXPORTS = {

@@ -390,7 +390,8 @@ struct Consts {
     int F, T2, R, S, IS, aa, double_side;
     int dist, alpha, tex;  // mode ids (read only by the GEN=true instantiations)
     int vec_store;         // 1: forward may use the shared-staged 128-bit store epilogue (alignment checked on host)
-    size_t tex_bs;         // elements between the textures (and texture gradients) of consecutive images; 0 = batch-shared
+    size_t tex_bs;         // elements per texture (F*T2*3)
+    int tex_div;           // consecutive images sharing one texture (1: per-image, B: one batch-shared texture)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(CTA, GEN ? 3 : 4) k_raster_fwd(const float* __
         issue_chunk(rec_img, s_list, n, 0, s_rec);
         issue_chunk(rec_img, s_list, n, 1, s_rec);
     }
-    const float* tex_img = textures + (size_t)b * K.tex_bs;
+    const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
     // torch-1.1 affine_grid (align_corners=True) coordinates of this pixel: linspace(-1, 1, S)
     const float gstep = 2.f / (float)(S - 1);
     const float gx = (px * 2 < S) ? (-1.f + gstep * px) : (1.f - gstep * (S - 1 - px));
@@ -896,8 +897,8 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd(const float* __restrict__
         ssum = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
         smax = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
     }
-    const float* tex_img = textures + (size_t)b * K.tex_bs;
-    float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * K.tex_bs : nullptr;
+    const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
+    float* gtex_img = TEXGRAD ? grad_tex + (size_t)(b / K.tex_div) * K.tex_bs : nullptr;
 
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % NSTAGE;
@@ -1249,8 +1250,8 @@ __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all
         for (int k = 0; k < 10; ++k) s_pix[k][pi] = v[k];
     }
     const int ncol = min(PT, S - x0), nrow = min(PT, S - y0);  // live extent of the tile
-    const float* tex_img = textures + (size_t)b * K.tex_bs;
-    float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * K.tex_bs : nullptr;
+    const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
+    float* gtex_img = TEXGRAD ? grad_tex + (size_t)(b / K.tex_div) * K.tex_bs : nullptr;
 
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % NSTAGE;
@@ -1456,6 +1457,7 @@ static int check_params(const UmrRasterParams* p) {
         p->texture_sample_type < 0 || p->texture_sample_type > 1)
         return UMR_ERR_UNSUPPORTED;
     if (p->texture_sample_type == UMR_TEX_VERTEX && p->texture_size != 3) return UMR_ERR_BAD_ARG;  // [B,F,3,3]
+    if (p->shared_textures > 1 && p->batch_size % p->shared_textures != 0) return UMR_ERR_BAD_ARG;
     if (p->func_id_rgb != UMR_RGB_HARD && p->func_id_rgb != UMR_RGB_SOFTMAX) return UMR_ERR_UNSUPPORTED;
     return UMR_OK;
 }
@@ -1489,7 +1491,8 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.alpha = p->func_id_alpha;
     K.tex = p->texture_sample_type;
     K.vec_store = 0;
-    K.tex_bs = p->shared_textures ? 0 : (size_t)p->num_faces * p->texture_size * 3;
+    K.tex_bs = (size_t)p->num_faces * p->texture_size * 3;
+    K.tex_div = p->shared_textures > 1 ? p->shared_textures : 1;
     return K;
 }
 
@@ -1655,7 +1658,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
     if (e != cudaSuccess) return (int)e;
     if (grad_textures) {
-        e = cudaMemsetAsync(grad_textures, 0, (size_t)(p->shared_textures ? F : n) * p->texture_size * 3 * sizeof(float), stream);
+        e = cudaMemsetAsync(grad_textures, 0, (size_t)(n / (p->shared_textures > 1 ? p->shared_textures : 1)) * p->texture_size * 3 * sizeof(float), stream);
         if (e != cudaSuccess) return (int)e;
     }
     const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
     const uint16_t* cl = clist + cidx * F;
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const float* tex_img = textures + (size_t)b * K.tex_bs;
+    const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
     const float ext0 = s_ext[0], ext1 = s_ext[1], ext2 = s_ext[2], ext3 = s_ext[3];
 
     // pixel state (kernel.cu:335-348)

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
     const uint16_t* cl = clist + cidx * F;
     const float4* box = box_all + (size_t)b * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    const float* tex_img = textures + (size_t)b * K.tex_bs;
+    const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
     const float ext0 = s_ext[0], ext1 = s_ext[1], ext2 = s_ext[2], ext3 = s_ext[3];
 
     // pixel state (kernel.cu:335-348)
@@ -680,8 +680,8 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
         for (int k = 0; k < 10; ++k) s_pix[k][tid] = v[k];
     }
     __syncthreads();
-    const float* tex_img = textures + (size_t)b * K.tex_bs;
-    float* gtex_img = TEXGRAD ? grad_tex + (size_t)b * K.tex_bs : nullptr;
+    const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
+    float* gtex_img = TEXGRAD ? grad_tex + (size_t)(b / K.tex_div) * K.tex_bs : nullptr;
     float* gf_img = grad_faces + (size_t)b * F * 9;
 
     float acc[9];

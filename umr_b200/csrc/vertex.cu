@@ -83,13 +83,14 @@ struct LightCfg {
 
 __global__ void __launch_bounds__(256) k_project_faces(const float* __restrict__ verts, const float* __restrict__ cams,
                                                        const int32_t* __restrict__ faces, float* __restrict__ fv,
-                                                       float* __restrict__ light, int V, int F, int64_t faces_bstride,
+                                                       float* __restrict__ light, int V, int F, int H, int64_t faces_bstride,
                                                        ProjCfg pc, LightCfg lc) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (f >= F) return;
     const Cam k = load_cam(cams, b);
-    const int32_t* fi = faces + (size_t)b * faces_bstride + (size_t)f * 3;
+    const int vb = b / H;  // vertex / face batch item: H consecutive renders (camera hypotheses) share one mesh
+    const int32_t* fi = faces + (size_t)vb * faces_bstride + (size_t)f * 3;
     float out[9], pre[9];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) k_project_faces(const float* __restrict__
             pre[3 * c] = pre[3 * c + 1] = pre[3 * c + 2] = nan;
             continue;
         }
-        const float* p = verts + ((size_t)b * V + v) * 3;
+        const float* p = verts + ((size_t)vb * V + v) * 3;
         project(k, pc, __ldg(p), __ldg(p + 1), __ldg(p + 2), out + 3 * c, pre + 3 * c);
     }
     float* o = fv + ((size_t)b * F + f) * 9;
@@ -125,11 +126,12 @@ __global__ void __launch_bounds__(256) k_project_faces(const float* __restrict__
 __global__ void __launch_bounds__(256) k_scatter_face_grads(const float* __restrict__ verts, const float* __restrict__ cams,
                                                             const int32_t* __restrict__ faces, const float* __restrict__ gfv,
                                                             const float* __restrict__ glight, float* __restrict__ gproj,
-                                                            int V, int F, int64_t faces_bstride, ProjCfg pc, LightCfg lc) {
+                                                            int V, int F, int H, int64_t faces_bstride, ProjCfg pc, LightCfg lc) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (f >= F) return;
-    const int32_t* fi = faces + (size_t)b * faces_bstride + (size_t)f * 3;
+    const int vb = b / H;  // vertex / face batch item: H consecutive renders (camera hypotheses) share one mesh
+    const int32_t* fi = faces + (size_t)vb * faces_bstride + (size_t)f * 3;
     int vid[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) vid[c] = __ldg(fi + c);
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) k_scatter_face_grads(const float* __restr
             float out[9], pre[9];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float* p = verts + ((size_t)b * V + vid[c]) * 3;
+                const float* p = verts + ((size_t)vb * V + vid[c]) * 3;
                 project(k, pc, __ldg(p), __ldg(p + 1), __ldg(p + 2), out + 3 * c, pre + 3 * c);
             }
             const float ax = pre[6] - pre[3], ay = pre[7] - pre[4], az = pre[8] - pre[5];
@@ -193,13 +195,14 @@ __global__ void __launch_bounds__(256) k_scatter_face_grads(const float* __restr
 // backward B: per vertex -> grad_vertices (direct store) and grad_cams (block reduce + 7 atomics)
 __global__ void __launch_bounds__(256) k_project_backward(const float* __restrict__ verts, const float* __restrict__ cams,
                                                           const float* __restrict__ gproj, float* __restrict__ gverts,
-                                                          float* __restrict__ gcams, int V, ProjCfg pc) {
+                                                          float* __restrict__ gcams, int V, int H, ProjCfg pc) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
+    const int vb = b / H;  // H consecutive renders (camera hypotheses) share one vertex set
     float gc[7] = {0, 0, 0, 0, 0, 0, 0};
     if (v < V) {
         const Cam k = load_cam(cams, b);
-        const float* p = verts + ((size_t)b * V + v) * 3;
+        const float* p = verts + ((size_t)vb * V + v) * 3;
         const float X = __ldg(p), Y = __ldg(p + 1), Z = __ldg(p + 2);
         const float* gp = gproj + ((size_t)b * V + v) * 3;
         float gx = __ldg(gp), gy = __ldg(gp + 1);
@@ -222,10 +225,12 @@ __global__ void __launch_bounds__(256) k_project_backward(const float* __restric
         const float c0 = q0 * q0 - vv;
         const float cx = vy * Gz - vz * Gy, cy = vz * Gx - vx * Gz, cz = vx * Gy - vy * Gx;  // v x G
         if (gverts != nullptr) {
-            float* o = gverts + ((size_t)b * V + v) * 3;
-            o[0] = c0 * Gx + 2.f * vG * vx - 2.f * q0 * cx;
-            o[1] = c0 * Gy + 2.f * vG * vy - 2.f * q0 * cy;
-            o[2] = c0 * Gz + 2.f * vG * vz - 2.f * q0 * cz;
+            float* o = gverts + ((size_t)vb * V + v) * 3;
+            const float o0 = c0 * Gx + 2.f * vG * vx - 2.f * q0 * cx;
+            const float o1 = c0 * Gy + 2.f * vG * vy - 2.f * q0 * cy;
+            const float o2 = c0 * Gz + 2.f * vG * vz - 2.f * q0 * cz;
+            if (H == 1) { o[0] = o0; o[1] = o1; o[2] = o2; }
+            else { atomicAdd(o, o0); atomicAdd(o + 1, o1); atomicAdd(o + 2, o2); }  // sum over the hypotheses (zero-filled by the host)
         }
         // dL/dq0 = G . (2 q0 X + 2 (v x X))
         const float wx = vy * Z - vz * Y, wy = vz * X - vx * Z, wz = vx * Y - vy * X;  // v x X
@@ -279,7 +284,9 @@ extern "C" int umr_project_faces_forward(const float* vertices, const float* cam
     cudaStream_t st = (cudaStream_t)stream_;
     const dim3 grid((p->num_faces + 255) / 256, p->batch_size);
     count_launch();
-    k_project_faces<<<grid, 256, 0, st>>>(vertices, cams, faces, face_vertices, light, p->num_vertices, p->num_faces,
+    const int H = p->num_hypotheses > 1 ? p->num_hypotheses : 1;
+    if (p->batch_size % H != 0) return UMR_ERR_BAD_ARG;
+    k_project_faces<<<grid, 256, 0, st>>>(vertices, cams, faces, face_vertices, light, p->num_vertices, p->num_faces, H,
                                           p->faces_batch_stride, make_pc(p), make_lc(p));
     return (int)cudaGetLastError();
 }
@@ -293,7 +300,11 @@ extern "C" int umr_project_faces_backward(const float* vertices, const float* ca
     if (p->batch_size > 65535) return UMR_ERR_TOO_LARGE;
     cudaStream_t st = (cudaStream_t)stream_;
     const int B = p->batch_size, V = p->num_vertices, F = p->num_faces;
+    const int H = p->num_hypotheses > 1 ? p->num_hypotheses : 1;
+    if (B % H != 0) return UMR_ERR_BAD_ARG;
     cudaError_t e = cudaMemsetAsync(grad_proj, 0, (size_t)B * V * 3 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    if (H > 1 && grad_vertices) e = cudaMemsetAsync(grad_vertices, 0, (size_t)(B / H) * V * 3 * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     if (grad_cams) {
         e = cudaMemsetAsync(grad_cams, 0, (size_t)B * 7 * sizeof(float), st);
@@ -301,9 +312,9 @@ extern "C" int umr_project_faces_backward(const float* vertices, const float* ca
     }
     count_launch(2);
     k_scatter_face_grads<<<dim3((F + 255) / 256, B), 256, 0, st>>>(vertices, cams, faces, grad_face_vertices, grad_light,
-                                                                   grad_proj, V, F, p->faces_batch_stride, make_pc(p),
+                                                                   grad_proj, V, F, H, p->faces_batch_stride, make_pc(p),
                                                                    make_lc(p));
-    k_project_backward<<<dim3((V + 255) / 256, B), 256, 0, st>>>(vertices, cams, grad_proj, grad_vertices, grad_cams, V,
+    k_project_backward<<<dim3((V + 255) / 256, B), 256, 0, st>>>(vertices, cams, grad_proj, grad_vertices, grad_cams, V, H,
                                                                  make_pc(p));
     return (int)cudaGetLastError();
 }

@@ -230,7 +230,9 @@ class MultiMaskLoss(nn.Module):
 
     def forward(self, vs, fs, cams_all_hypo, cam_probs, masks_gt):
         H = self.num_hypo_cams
-        rgba, _, _ = self.renderer.forward(tile_hypotheses(vs, H), tile_hypotheses(fs, H), cams_all_hypo.view(-1, 7))
+        # vertices / faces are NOT repeated per hypothesis (the reference materialises repeat(1, 8, ...) copies,
+        # loss_utils.py:260-261): the vertex kernel broadcasts each mesh over its H cameras
+        rgba, _, _ = self.renderer.forward(vs, fs, cams_all_hypo.view(-1, 7))
         mask_all_hypo = rgba[:, 3, :, :]
         per_render = neg_iou_loss(mask_all_hypo, tile_hypotheses(masks_gt, H), avg=False)
         return expected_over_hypotheses(per_render, cam_probs), mask_all_hypo
@@ -261,8 +263,9 @@ class MultiTextureLoss(nn.Module):
                 dts_barrier):
         H = self.num_hypo_cams
         # textured softmax render of every hypothesis; vertices detached: only the texture learns here (:313)
-        texture_rgba, _, _ = self.renderer.forward(tile_hypotheses(vs.detach(), H), tile_hypotheses(fs, H),
-                                                   cams_all_hypo.view(-1, 7), tile_hypotheses(tx, H))
+        # ... and neither is the [B*8,F,T2,3] texture copy of loss_utils.py:305 (70.8 MB at batch 16): the raster kernels
+        # read textures[b // 8] and accumulate the 8 hypotheses' texture gradients directly
+        texture_rgba, _, _ = self.renderer.forward(vs.detach(), fs, cams_all_hypo.view(-1, 7), tx)
         texture_pred = texture_rgba[:, 0:3, :, :]
         per_render = self.texture_loss(texture_pred, tile_hypotheses(rgbs, H), tile_hypotheses(masks_gt, H),
                                        masks_pred, avg=False)

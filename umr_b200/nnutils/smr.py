@@ -80,11 +80,13 @@ class SoftRenderer(torch.nn.Module):
         B, F = fv.shape[:2]
         if light is not None:
             # ones * light == light; textures * light[:, :, None, :] as in lighting.py:57
+            if textures is not None and textures.shape[0] not in (1, B):   # hypothesis-shared textures meet a per-render light
+                textures = textures.repeat_interleave(B // textures.shape[0], dim=0)
             tex = light[:, :, None, :] if textures is None else textures * light[:, :, None, :]
         else:
             c = [float(amb.light_intensity) * float(k) for k in amb.light_color]
             if textures is None:
-                tex = torch.tensor(c, dtype=torch.float32, device=fv.device).view(1, 1, 1, 3).expand(B, F, 1, 3)
+                tex = torch.tensor(c, dtype=torch.float32, device=fv.device).view(1, 1, 1, 3).expand(1, F, 1, 3)  # one texture shared by the batch
             elif c == [1.0, 1.0, 1.0]:
                 tex = textures  # x * 1 == x
             else:
@@ -92,8 +94,18 @@ class SoftRenderer(torch.nn.Module):
         return r.rasterizer.rasterize(fv, tex)
 
     def forward(self, vertices, faces, cams, textures=None):
+        """vertices [B,V,3], faces [B,F,3], cams [B,7], textures [B,F,T2,3] | None, as the reference (smr.py:80-87).
+        Extension: `cams` may hold H camera hypotheses per mesh -- cams [B*H,7] with vertices / faces
+        [B,...] and textures [B,...] (or [1,...]) NOT repeated; the kernels broadcast instead of the reference's
+        repeat(1, 8, ...) copies (loss_utils.py:260-261, 303-305).  Returns B*H renders."""
         if self._fusable(vertices):
             return self._forward_fused(vertices, faces, cams, textures)
+        H = cams.shape[0] // vertices.shape[0]
+        if H > 1:  # generic torch path: materialise the copies like the reference
+            vertices = vertices.repeat_interleave(H, dim=0)
+            faces = faces.repeat_interleave(H, dim=0) if faces.dim() == 3 and faces.shape[0] > 1 else faces
+            if textures is not None and textures.shape[0] > 1:
+                textures = textures.repeat_interleave(cams.shape[0] // textures.shape[0], dim=0)
         faces = faces.int()
         verts = self.proj_fn(vertices, cams, offset_z=self.offset_z)
         if textures is not None:

@@ -145,16 +145,20 @@ class SoftRasterizeFunction(torch.autograd.Function):
         fv = face_vertices.detach().reshape(B, F, 9).contiguous().float()
         # a [1,F,T2,3] texture with B > 1 is a batch-SHARED parameter: the kernels read the one copy for every image and
         # accumulate its gradient directly (the reference materialises repeat(B,...) copies, loss_utils.py:305)
-        shared = textures.shape[0] == 1 and B > 1
-        if textures.shape[0] != B and not shared:
-            raise ValueError("textures batch %d does not match face_vertices batch %d" % (textures.shape[0], B))
+        # fewer textures than renders: every B / Bt consecutive renders share one texture -- Bt == 1: a batch-shared
+        # parameter; Bt == B / 8: the 8 camera hypotheses of each sample (the reference materialises repeat(...) copies,
+        # loss_utils.py:305).  The kernels index textures[b // group] and accumulate the group's gradient directly.
+        Bt = textures.shape[0]
+        if Bt != B and (Bt <= 0 or B % Bt != 0):
+            raise ValueError("textures batch %d does not divide face_vertices batch %d" % (Bt, B))
+        group = B // Bt
         tex = textures.detach().contiguous().float()
         T2 = tex.shape[2]
         S = int(image_size) * (2 if anti_aliasing else 1)
         params = make_params(B, F, T2, image_size, anti_aliasing, background_color, near, far, fill_back,
                              eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb,
                              aggr_func_alpha, texture_type)
-        params.shared_textures = 1 if shared else 0
+        params.shared_textures = group if group > 1 else 0
         need_bwd = face_vertices.requires_grad or textures.requires_grad
         _attach_events(params, "fwd")
         with torch.cuda.device(dev):

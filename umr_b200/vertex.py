@@ -11,12 +11,13 @@ from . import _lib
 from .raster import _ptr, _stream_ptr
 
 
-def make_project_params(B, V, F, faces_bstride, offset_z, eye_z, viewing_scale, flip_y, light):
+def make_project_params(B, V, F, faces_bstride, offset_z, eye_z, viewing_scale, flip_y, light, hypotheses=1):
     p = _lib.UmrProjectParams()
     p.batch_size, p.num_vertices, p.num_faces = B, V, F
     p.flip_y = 1 if flip_y else 0
     p.faces_batch_stride = faces_bstride
     p.offset_z, p.eye_z, p.viewing_scale = float(offset_z), float(eye_z), float(viewing_scale)
+    p.num_hypotheses = int(hypotheses)
     if light is None:
         p.light_enabled = 0
     else:
@@ -40,12 +41,18 @@ class ProjectFacesFunction(torch.autograd.Function):
         v = vertices.detach().contiguous().float()
         c = cams.detach().contiguous().float()
         f = faces if (faces.dtype == torch.int32 and faces.is_contiguous()) else faces.int().contiguous()
-        B, V = v.shape[:2]
+        Bv, V = v.shape[:2]
+        B = c.shape[0]                       # renders = cameras; Bv meshes, B / Bv camera hypotheses each
+        if B % Bv != 0:
+            raise ValueError("cams batch %d is not a multiple of the vertices batch %d" % (B, Bv))
+        H = B // Bv
         if f.dim() == 2:
             F, fstride = f.shape[0], 0
         else:
+            if f.shape[0] not in (1, Bv):
+                raise ValueError("faces batch %d does not match the vertices batch %d" % (f.shape[0], Bv))
             F, fstride = f.shape[1], (f.shape[1] * 3 if f.shape[0] > 1 else 0)
-        params = make_project_params(B, V, F, fstride, offset_z, eye_z, viewing_scale, flip_y, light)
+        params = make_project_params(B, V, F, fstride, offset_z, eye_z, viewing_scale, flip_y, light, H)
         with torch.cuda.device(dev):
             fv = torch.empty(B, F, 3, 3, device=dev, dtype=torch.float32)
             lt = torch.empty(B, F, 3, device=dev, dtype=torch.float32) if light is not None else None
@@ -66,7 +73,8 @@ class ProjectFacesFunction(torch.autograd.Function):
         lib = _lib.load()
         v, c, f = ctx.saved_tensors
         dev = v.device
-        B, V = v.shape[:2]
+        V = v.shape[1]
+        B = c.shape[0]
         with torch.cuda.device(dev):
             if g_fv is None:
                 g_fv = torch.zeros(B, ctx.params.num_faces, 9, device=dev, dtype=torch.float32)
