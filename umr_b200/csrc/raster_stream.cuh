@@ -717,36 +717,71 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
         uint32_t k = kbeg, kwin = kbeg;
         uint32_t hw = (kbeg + lane < kend) ? __ldg(hdrs + kbeg + lane) : 0u;
         int o = 0;
-        while (k < kend) {
-            if (k >= kwin + 32u) {  // warp-uniform
-                kwin = k;
-                hw = (k + lane < kend) ? __ldg(hdrs + k + lane) : 0u;
-            }
-            const uint32_t wend = min(kend, kwin + 32u);  // chains stop at the header window
-            const int rel = (int)(k - kwin);
-            const uint32_t h0 = __shfl_sync(0xffffffffu, hw, rel), h1 = __shfl_sync(0xffffffffu, hw, (rel + 1) & 31);
-            const uint32_t h2 = __shfl_sync(0xffffffffu, hw, (rel + 2) & 31), h3 = __shfl_sync(0xffffffffu, hw, (rel + 3) & 31);
-            const int a0 = (int)(h0 >> 16) - o;
-            if (a0 <= 0) { ++k; o = 0; continue; }  // block exhausted / empty (warp-uniform)
-            const int f = (int)(h0 & 0xffffu);
-            // records available in the following blocks while they belong to the same face (an empty block is transparent)
-            int a1 = 0, a2 = 0, a3 = 0, nchain = 1;
-            if (k + 1 < wend && ((h1 >> 16) == 0 || (int)(h1 & 0xffffu) == f)) {
-                a1 = (int)(h1 >> 16); nchain = 2;
-                if (k + 2 < wend && ((h2 >> 16) == 0 || (int)(h2 & 0xffffu) == f)) {
-                    a2 = (int)(h2 >> 16); nchain = 3;
-                    if (k + 3 < wend && ((h3 >> 16) == 0 || (int)(h3 & 0xffffu) == f)) { a3 = (int)(h3 >> 16); nchain = 4; }
+        // plan(): the next step of the stream -- its face, whether this lane carries a record, and where the record is --
+        // and advance (k, o).  Planning runs one step AHEAD of the arithmetic so that the step's three 16-byte lines per lane
+        // can be prefetched into L1 while the previous step is being processed (the kernel was bound by the latency of
+        // these loads: 50 % of its stall samples, profiles/r02_*bwd2*).
+        auto plan = [&](int& f_out, bool& act_out, const float4*& src_out) -> bool {
+            while (k < kend) {
+                if (k >= kwin + 32u) {  // warp-uniform
+                    kwin = k;
+                    hw = (k + lane < kend) ? __ldg(hdrs + k + lane) : 0u;
                 }
-            }
-            const int p1 = a0, p2 = a0 + a1, p3 = p2 + a2, p4 = p3 + a3;
-            if (f != cur_f) { flush(); cur_f = f; }
-            if (lane < p4) {
+                const uint32_t wend = min(kend, kwin + 32u);  // chains stop at the header window
+                const int rel = (int)(k - kwin);
+                const uint32_t h0 = __shfl_sync(0xffffffffu, hw, rel), h1 = __shfl_sync(0xffffffffu, hw, (rel + 1) & 31);
+                const uint32_t h2 = __shfl_sync(0xffffffffu, hw, (rel + 2) & 31), h3 = __shfl_sync(0xffffffffu, hw, (rel + 3) & 31);
+                const int a0 = (int)(h0 >> 16) - o;
+                if (a0 <= 0) { ++k; o = 0; continue; }  // block exhausted / empty (warp-uniform)
+                const int f = (int)(h0 & 0xffffu);
+                // records available in the following blocks while they belong to the same face (an empty block is transparent)
+                int a1 = 0, a2 = 0, a3 = 0, nchain = 1;
+                if (k + 1 < wend && ((h1 >> 16) == 0 || (int)(h1 & 0xffffu) == f)) {
+                    a1 = (int)(h1 >> 16); nchain = 2;
+                    if (k + 2 < wend && ((h2 >> 16) == 0 || (int)(h2 & 0xffffu) == f)) {
+                        a2 = (int)(h2 >> 16); nchain = 3;
+                        if (k + 3 < wend && ((h3 >> 16) == 0 || (int)(h3 & 0xffffu) == f)) { a3 = (int)(h3 >> 16); nchain = 4; }
+                    }
+                }
+                const int p1 = a0, p2 = a0 + a1, p3 = p2 + a2, p4 = p3 + a3;
                 int bi, pos;
                 if (lane < p1) { bi = 0; pos = lane + o; }
                 else if (lane < p2) { bi = 1; pos = lane - p1; }
                 else if (lane < p3) { bi = 2; pos = lane - p2; }
                 else { bi = 3; pos = lane - p3; }
-                const float4* src = pb.recs + (size_t)(seg + 2 + k + bi) * BLK_F4 + pos;
+                f_out = f;
+                act_out = lane < p4;
+                src_out = pb.recs + (size_t)(seg + 2 + k + bi) * BLK_F4 + pos;
+                // advance the stream by min(32, p4) records: blocks consumed completely, then a partial one
+                int left = min(32, p4), i = 0;
+                const int av[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (i == q && q < nchain && left >= av[q]) { left -= av[q]; ++i; }
+                }
+                k += (uint32_t)i;
+                o = (i == 0) ? o + left : ((i < nchain) ? left : 0);
+                return true;
+            }
+            return false;
+        };
+        auto prefetch = [&](const float4* p) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
+        };
+        int f_c = 0, f_n = 0;
+        bool act_c = false, act_n = false;
+        const float4 *src_c = nullptr, *src_n = nullptr;
+        bool have = plan(f_c, act_c, src_c);
+        if (have && act_c) prefetch(src_c);
+        while (have) {
+            const bool have_n = plan(f_n, act_n, src_n);
+            if (have_n && act_n) prefetch(src_n);
+            const int f = f_c;
+            if (f != cur_f) { flush(); cur_f = f; }
+            if (act_c) {
+                const float4* src = src_c;
                 const float4 r0 = __ldg(src), r1 = __ldg(src + 32), r2 = __ldg(src + 64);
                 const float D = r0.x, sdx = r0.y, sdy = r0.z, zn = r0.w;  // zn: normalised depth exactly as the forward formed it
                 const uint32_t meta = __float_as_uint(r1.w);
@@ -803,17 +838,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                 acc[6] += q * r1.z * sdx;
                 acc[7] += q * r1.z * sdy;
             }
-            // advance the stream by min(32, p4) records: blocks consumed completely, then a partial one
-            {
-                int left = min(32, p4), i = 0;
-                const int av[4] = {a0, a1, a2, a3};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (i == q && q < nchain && left >= av[q]) { left -= av[q]; ++i; }
-                }
-                k += (uint32_t)i;
-                o = (i == 0) ? o + left : ((i < nchain) ? left : 0);
-            }
+            f_c = f_n; act_c = act_n; src_c = src_n; have = have_n;
         }
         seg = next;
     }
