@@ -1412,11 +1412,26 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs_list(const float* _
 
 #include "raster_stream.cuh"
 #include "raster_fwd3.cuh"
+#include "raster_fwd4.cuh"
 
 // =============================================================================================
 // C ABI
 // =============================================================================================
 using namespace umr;
+
+// Which forward serves the UMR configuration: 4 = k_raster_fwd4 (32x32 tiles, dynamic 8x4 pixel blocks; tile list in
+// shared memory sized by F), 3 = k_raster_fwd3 (16x16 tiles, windowed list: any F), 2 = k_raster_fwd2 (pair-parallel,
+// kept for A/B).  Forward and backward must agree (the pair records' pixel index is relative to the forward's tile).
+static int forward_impl(int F) {
+    static const int forced = [] {
+        const char* e = getenv("UMR_FWD_IMPL");  // "pairs" | "tile16" | unset
+        if (e && e[0] == 'p' && e[1] == 'a') return 2;
+        if (e && e[0] == 't' && e[1] == 'i') return 3;
+        return 0;
+    }();
+    if (forced) return forced;
+    return F <= FWD4_MAX_F ? 4 : 3;
+}
 
 extern "C" size_t umr_raster_workspace_bytes(int32_t B, int32_t F, int32_t image_size, int32_t anti_aliasing) {
     if (B <= 0 || F <= 0 || image_size <= 0) return 0;
@@ -1516,6 +1531,7 @@ static int ensure_smem_attrs() {
     if (e != cudaSuccess) return (int)e;
     UMR_SET((k_raster_fwd<0, true>)) UMR_SET((k_raster_fwd<1, true>))
     UMR_SET((k_raster_fwd2<0>)) UMR_SET((k_raster_fwd2<1>))
+    UMR_SET((k_raster_fwd4<0>)) UMR_SET((k_raster_fwd4<1>))
     UMR_SET((k_raster_bwd<0, false, false>)) UMR_SET((k_raster_bwd<0, true, false>))
     UMR_SET((k_raster_bwd<1, false, false>)) UMR_SET((k_raster_bwd<1, true, false>))
     UMR_SET((k_raster_bwd<0, false, true>)) UMR_SET((k_raster_bwd<0, true, true>))
@@ -1583,18 +1599,19 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
         count_launch(2);
         k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
         if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
-        static const bool fwd_pairs = [] {  // UMR_FWD_IMPL=pairs selects the pair-parallel forward (A/B testing)
-            const char* e = getenv("UMR_FWD_IMPL");
-            return e && e[0] == 'p' && e[1] == 'a';
-        }();
+        const int impl = forward_impl(F);
 #define UMR_FWD_ARGS rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc, ubox, K, p->eps, \
                      p->background_color[0], p->background_color[1], p->background_color[2], pb, ncb
-        if (fwd_pairs) {
+        if (impl == 2) {
             if (softmax) k_raster_fwd2<1><<<grid, CTA, fwd2_smem, stream>>>(UMR_FWD_ARGS);
             else k_raster_fwd2<0><<<grid, CTA, fwd2_smem, stream>>>(UMR_FWD_ARGS);
-        } else {
+        } else if (impl == 3) {
             if (softmax) k_raster_fwd3<1><<<grid, CTA, 0, stream>>>(UMR_FWD_ARGS);
             else k_raster_fwd3<0><<<grid, CTA, 0, stream>>>(UMR_FWD_ARGS);
+        } else {
+            const dim3 grid32((K.S + T4 - 1) / T4, (K.S + T4 - 1) / T4, B);
+            if (softmax) k_raster_fwd4<1><<<grid32, CTA, fwd4_dyn_smem(F), stream>>>(UMR_FWD_ARGS);
+            else k_raster_fwd4<0><<<grid32, CTA, fwd4_dyn_smem(F), stream>>>(UMR_FWD_ARGS);
         }
 #undef UMR_FWD_ARGS
         if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
@@ -1676,8 +1693,12 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         else if (use_pairs) {                                                                                 \
             if (pb.cap > 0) {                                                                                 \
                 count_launch();                                                                               \
-                k_raster_bwd2<RGBM, TG><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images,  \
-                                                                        grad_faces, grad_textures, K, pb);    \
+                if (forward_impl(F) == 4)                                                                     \
+                    k_raster_bwd2<RGBM, TG, 32><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                                                                            grad_faces, grad_textures, K, pb); \
+                else                                                                                          \
+                    k_raster_bwd2<RGBM, TG, 16><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                                                                            grad_faces, grad_textures, K, pb); \
             }                                                                                                 \
             if (pb.cap > 0)                                                                                   \
                 k_raster_bwd_pairs_list<RGBM, TG><<<list_grid, CTA, smem, stream>>>(                          \
@@ -1692,6 +1713,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
                                                                        grad_images, grad_faces, grad_textures, ubox, K); \
     } while (0)
     const dim3 grid_pairs((K.S + PT - 1) / PT, (K.S + PT - 1) / PT, B);
+    const dim3 grid32((K.S + T4 - 1) / T4, (K.S + T4 - 1) / T4, B);
     const size_t ntiles = (size_t)grid_pairs.x * grid_pairs.y * B;
     const unsigned list_grid = (unsigned)(ntiles < 444 ? ntiles : 444);  // 3 CTAs x 148 SMs walk the unsaved-tile list
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);

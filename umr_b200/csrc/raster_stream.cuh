@@ -643,21 +643,23 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
 // ---------------------------------------------------------------------------------------------
 // backward: stream the saved pair records of the tile
 // ---------------------------------------------------------------------------------------------
-template <int RGB, bool TEXGRAD>
+// TS: side of the forward's tile (16: k_raster_fwd3 / k_raster_fwd2, 32: k_raster_fwd4); one CTA streams one tile
+template <int RGB, bool TEXGRAD, int TS>
 __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                         const float* __restrict__ aggrs, const float* __restrict__ grad_images,
                                                         float* __restrict__ grad_faces, float* __restrict__ grad_tex, Consts K,
                                                         PairBuf pb) {
-    __shared__ float s_pix[10][TILE * TILE];  // g0..g3, C0..C3, ssum, smax (row-major tile pixels)
+    __shared__ float s_pix[10][TS * TS];  // g0..g3, C0..C3, ssum, smax (row-major tile pixels)
+    constexpr int NP = TS * TS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int S = K.S, F = K.F;
     const size_t tile_id = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const int32_t head = __ldg(pb.tile_head + tile_id);
     if (head < 0) return;  // empty, or unsaved (k_raster_bwd_pairs handles it)
-    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
-    {
-        const int px = x0 + (tid % TILE), py = y0 + (tid / TILE);
+    const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+    for (int pi = tid; pi < NP; pi += CTA) {
+        const int px = x0 + (pi % TS), py = y0 + (pi / TS);
         const size_t np = (size_t)S * S;
         float v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
         if (px < S && py < S) {
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
             v[9] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
         }
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s_pix[k][tid] = v[k];
+        for (int k = 0; k < 10; ++k) s_pix[k][pi] = v[k];
     }
     __syncthreads();
     const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
@@ -785,27 +787,28 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                 const float4 r0 = __ldg(src), r1 = __ldg(src + 32), r2 = __ldg(src + 64);
                 const float D = r0.x, sdx = r0.y, sdy = r0.z, zn = r0.w;  // zn: normalised depth exactly as the forward formed it
                 const uint32_t meta = __float_as_uint(r1.w);
-                const int pix = (int)(meta & 0xffu), tix = (int)((meta >> 8) & 0xffffu);
+                const int pix = TS == 16 ? (int)(meta & 0xffu) : (int)(meta & 0x3ffu);
+                const int tix = TS == 16 ? (int)((meta >> 8) & 0xffffu) : (int)((meta >> 10) & 0x3fffu);
                 const bool front = (meta >> 24) & 1u;
                 const float* sp = &s_pix[0][pix];
-                const float g3 = sp[3 * 256];
-                const float one_m_a = 1 - sp[7 * 256];
+                const float g3 = sp[3 * NP];
+                const float one_m_a = 1 - sp[7 * NP];
                 // g3 * ((1 - alpha) / max(1 - D, 1e-6)) (kernel.cu:584), in fp32 (the reference promotes to double;
                 // gradients are compared at 1e-4, see DESIGN.md "backward arithmetic")
                 float Cxy = (one_m_a == 0.f || g3 == 0.f) ? g3 * one_m_a : g3 * __fdividef(one_m_a, fmaxf(1 - D, 1e-6f));
                 if (RGB == 0) {
-                    if ((float)f == sp[9 * 256]) {  // aggrs[1] = winning face id (:596)
+                    if ((float)f == sp[9 * NP]) {  // aggrs[1] = winning face id (:596)
                         if (TEXGRAD) {
                             float* gt = gtex_img + ((size_t)f * K.T2 + tix) * 3;
                             red_add_global(gt + 0, sp[0]);
-                            red_add_global(gt + 1, sp[1 * 256]);
-                            red_add_global(gt + 2, sp[2 * 256]);
+                            red_add_global(gt + 1, sp[1 * NP]);
+                            red_add_global(gt + 2, sp[2 * NP]);
                         }
                     }
                 } else if (front || K.double_side) {
-                    const float g0 = sp[0], g1 = sp[1 * 256], g2 = sp[2 * 256];
+                    const float g0 = sp[0], g1 = sp[1 * NP], g2 = sp[2 * NP];
                     if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
-                        const float s = __fdividef(D * expf((zn - sp[9 * 256]) * K.r_gamma), sp[8 * 256]);  // :608
+                        const float s = __fdividef(D * expf((zn - sp[9 * NP]) * K.r_gamma), sp[8 * NP]);  // :608
                         if (s != 0.f) {
                             const size_t to = ((size_t)f * K.T2 + tix) * 3;
                             if (TEXGRAD) {
@@ -814,9 +817,9 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                                 red_add_global(gtex_img + to + 2, s * g2);
                             }
                             float Crgb = 0.f;
-                            Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * 256]);
-                            Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * 256]);
-                            Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * 256]);
+                            Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * NP]);
+                            Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * NP]);
+                            Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * NP]);
                             Crgb *= s;
                             if (Crgb != 0.f) {
                                 Cxy += __fdividef(Crgb, D);
