@@ -75,7 +75,9 @@ typedef struct UmrRasterParams {
      * summed over each group) are [B/G,F,T2,3].  G == B: one batch-shared parameter; G == 8: the camera hypotheses of a
      * sample (the reference materialises repeat(...) copies, loss_utils.py:305: 70.8 MB at batch 16).  0 or 1: per-image. */
     int32_t shared_textures;
-    int32_t reserved_;
+    /* forward tiling: 0 = automatic (by grid size), 16 = 16x16 tiles with one warp per 8x4 pixel block, 32 = 32x32 tiles
+     * whose warps grab pixel blocks dynamically (F <= 2048).  Must be the same in the matching backward call. */
+    int32_t tile_mode;
 } UmrRasterParams;
 
 const char* umr_error_string(int code);

@@ -81,8 +81,10 @@ BASELINE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("tile", [16, 32])
 @pytest.mark.parametrize("name,B,subdiv,tex_res,image_size,rgb", BASELINE_CASES)
-def test_parity_at_baseline_shapes(name, B, subdiv, tex_res, image_size, rgb):
+def test_parity_at_baseline_shapes(name, B, subdiv, tex_res, image_size, rgb, tile, monkeypatch):
+    monkeypatch.setattr(raster, "FORWARD_TILE", tile)   # both forward kernels at the BASELINE shapes
     fv, tex = scene(B, subdiv, tex_res, seed=1000 + image_size)
     g = np.random.default_rng(17).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
     ref = run_oracle(fv, tex, image_size, True, rgb, g)

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _run(fv, tex, image_size, rgb, g, cand_per_pixel):
-    old = raster.PAIR_CAND_PER_PIXEL
+def _run(fv, tex, image_size, rgb, g, cand_per_pixel, tile=0):
+    old, old_tile = raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE
     raster.PAIR_CAND_PER_PIXEL = cand_per_pixel
+    raster.FORWARD_TILE = tile
     try:
         tfv = torch.from_numpy(fv).to(DEV).requires_grad_(True)
         ttex = torch.from_numpy(tex).to(DEV).requires_grad_(True)
@@ -29,19 +30,20 @@ def _run(fv, tex, image_size, rgb, g, cand_per_pixel):
         return dict(images=img.detach().cpu().numpy(), grad_faces=tfv.grad.cpu().numpy(), grad_tex=ttex.grad.cpu().numpy(),
                     stats=stats)
     finally:
-        raster.PAIR_CAND_PER_PIXEL = old
+        raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE = old, old_tile
 
 
+@pytest.mark.parametrize("tile", [16, 32])   # k_raster_fwd3 (16x16, static warps) / k_raster_fwd4 (32x32, dynamic pixel blocks)
 @pytest.mark.parametrize("rgb", ["softmax", "hard"])
 @pytest.mark.parametrize("B,subdiv,tex_res,image_size", [(2, 3, 3, 64), (1, 3, 6, 128), (1, 2, 2, 37)])
-def test_streamed_backward_matches_recompute_and_oracle(rgb, B, subdiv, tex_res, image_size):
+def test_streamed_backward_matches_recompute_and_oracle(tile, rgb, B, subdiv, tex_res, image_size):
     fv, tex = scene(B, subdiv, tex_res, seed=31 + image_size)
     g = np.random.default_rng(5).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
     ref = run_oracle(fv, tex, image_size, True, rgb, g)
-    full = _run(fv, tex, image_size, rgb, g, 32.0)    # everything saved
-    none = _run(fv, tex, image_size, rgb, g, 0.0)     # no pair buffer: recompute backward
-    part = _run(fv, tex, image_size, rgb, g, 0.7)     # buffer too small: some tiles saved, the rest recomputed
-    tiny = _run(fv, tex, image_size, rgb, g, 1e-4)    # nothing fits
+    full = _run(fv, tex, image_size, rgb, g, 32.0, tile)    # everything saved
+    none = _run(fv, tex, image_size, rgb, g, 0.0, tile)     # no pair buffer: recompute backward
+    part = _run(fv, tex, image_size, rgb, g, 0.7, tile)     # buffer too small: some tiles saved, the rest recomputed
+    tiny = _run(fv, tex, image_size, rgb, g, 1e-4, tile)    # nothing fits
     assert full["stats"][1] == 0 and full["stats"][0] > 0, full["stats"]
     assert none["stats"] is None
     assert part["stats"][1] > 0, "the partial-capacity case must leave tiles unsaved: %s" % (part["stats"],)
@@ -89,3 +91,23 @@ def test_batch_shared_texture_equals_repeated_copies(rgb, cand):
     assert outs[0][2].shape == (1,) + tex.shape[1:]
     ok, msg = rel_report("grad_tex (batch sum)", outs[0][2], outs[1][2], 1e-4, 1e-6 * float(np.abs(outs[1][2]).max()) + 1e-7)
     assert ok, msg
+
+
+@pytest.mark.parametrize("rgb", ["softmax", "hard"])
+def test_dense_mesh_takes_the_windowed_slow_path(rgb):
+    """5120 faces on a 64x64 raster: the single coarse bin lists every face -- longer than the 32x32-tile kernel's shared
+    tile list -- so its windowed static path runs (and leaves the tile to the recompute backward); results must not change."""
+    fv, tex = scene(1, 4, 1, seed=8)
+    assert fv.shape[1] == 5120
+    g = np.random.default_rng(6).normal(size=(1, 4, 32, 32)).astype(np.float32)
+    ref = run_oracle(fv, tex, 32, True, rgb, g)
+    a = _run(fv, tex, 32, rgb, g, 64.0, 32)
+    b = _run(fv, tex, 32, rgb, g, 64.0, 16)
+    assert a["stats"][1] > 0, "expected the dense tile to be left unsaved by the 32x32-tile kernel: %s" % (a["stats"],)
+    assert np.array_equal(a["images"], b["images"])
+    ok, msg = rel_report("images", a["images"], ref["images"], 1e-4, 1e-6)
+    assert ok, msg
+    at = 1e-6 * float(np.abs(ref["grad_faces"]).max() + 1e-30) + 1e-7
+    for got in (a, b):
+        ok, msg = rel_report("grad_faces", got["grad_faces"], ref["grad_faces"], 1e-4, at)
+        assert ok, msg

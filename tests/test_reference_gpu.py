@@ -68,9 +68,11 @@ def _three_way(mod, fv, tex, IS, rgb_name, rgb, check_tex_grad):
 
 
 @pytest.mark.skipif(_mods()[1] is None, reason="baseline/_ref/soft_rasterize_ref_nofma.so not built")
+@pytest.mark.parametrize("tile", [16, 32])
 @pytest.mark.parametrize("rgb_name,rgb", [("softmax", 1), ("hard", 0)])
-def test_bit_exact_at_c2_shape(rgb_name, rgb):
-    """BASELINE config 2 per-image shape: F=1280, 256^2 (S=512), T^2=36, B=2."""
+def test_bit_exact_at_c2_shape(rgb_name, rgb, tile, monkeypatch):
+    """BASELINE config 2 per-image shape: F=1280, 256^2 (S=512), T^2=36, B=2 -- through both forward kernels."""
+    monkeypatch.setattr(raster, "FORWARD_TILE", tile)
     fv, tex = rc.scene(2, 6, seed=3)
     _three_way(_mods()[1], fv, tex, 256, rgb_name, rgb, False)
 

@@ -1422,15 +1422,24 @@ using namespace umr;
 // Which forward serves the UMR configuration: 4 = k_raster_fwd4 (32x32 tiles, dynamic 8x4 pixel blocks; tile list in
 // shared memory sized by F), 3 = k_raster_fwd3 (16x16 tiles, windowed list: any F), 2 = k_raster_fwd2 (pair-parallel,
 // kept for A/B).  Forward and backward must agree (the pair records' pixel index is relative to the forward's tile).
-static int forward_impl(int F) {
+static int forward_impl(int F, int B, int S, int tile_mode) {
+    if (tile_mode == 16) return 3;
+    if (tile_mode == 32) return F <= FWD4_MAX_F ? 4 : 3;
     static const int forced = [] {
-        const char* e = getenv("UMR_FWD_IMPL");  // "pairs" | "tile16" | unset
+        const char* e = getenv("UMR_FWD_IMPL");  // "pairs" | "tile16" | "dynamic" | unset
         if (e && e[0] == 'p' && e[1] == 'a') return 2;
         if (e && e[0] == 't' && e[1] == 'i') return 3;
+        if (e && e[0] == 'd' && e[1] == 'y') return 4;   // "dynamic"
         return 0;
     }();
+    if (forced == 4) return F <= FWD4_MAX_F ? 4 : 3;
     if (forced) return forced;
-    return F <= FWD4_MAX_F ? 4 : 3;
+    // Automatic choice: the 16x16-tile kernel.  Same-box A/B on B200 (profiles/r02_tile_ab.txt): the 32x32-tile kernel with
+    // dynamic pixel blocks is 8 % faster at C3 (32 x 1024^2, F=1280), 8 % slower at C5 (8 x 2048^2, F=5120) and 30 % slower
+    // at C2 (16 x 512^2: only ~1600 of its 4096 tiles carry work -> 2.7 waves of heavy CTAs on 148 SMs x 4).  It stays
+    // available through UmrRasterParams.tile_mode = 32 (tested at every shape), but does not earn a heuristic.
+    (void)B; (void)S;
+    return 3;
 }
 
 extern "C" size_t umr_raster_workspace_bytes(int32_t B, int32_t F, int32_t image_size, int32_t anti_aliasing) {
@@ -1599,7 +1608,7 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
         count_launch(2);
         k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
         if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
-        const int impl = forward_impl(F);
+        const int impl = forward_impl(F, B, K.S, p->tile_mode);
 #define UMR_FWD_ARGS rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc, ubox, K, p->eps, \
                      p->background_color[0], p->background_color[1], p->background_color[2], pb, ncb
         if (impl == 2) {
@@ -1693,7 +1702,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         else if (use_pairs) {                                                                                 \
             if (pb.cap > 0) {                                                                                 \
                 count_launch();                                                                               \
-                if (forward_impl(F) == 4)                                                                     \
+                if (forward_impl(F, B, K.S, p->tile_mode) == 4)                                                                     \
                     k_raster_bwd2<RGBM, TG, 32><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
                                                                             grad_faces, grad_textures, K, pb); \
                 else                                                                                          \

@@ -9,17 +9,19 @@
 // k_raster_fwd3's: thread = pixel, faces in ascending index, records staged into a warp-private cp.async double buffer,
 // pair records emitted per (face, pixel block met), face-major inside the tile.
 //
-// The tile list lives in dynamic shared memory sized by F (a coarse bin's list cannot be longer), so the kernel is used
-// for F <= FWD4_MAX_F (k_raster_fwd3, which windows its list, serves larger meshes).
+// The tile list lives in shared memory (FWD4_CAP entries).  A tile whose coarse-bin list is longer than that (a very
+// dense mesh region) takes the SLOW path: the list is processed in windows with a static block assignment (4 passes of
+// 8 blocks, pixel state kept in registers across the windows of a pass) and the tile is left to the recompute backward.
 #pragma once
 
 namespace umr {
 
 constexpr int T4 = 32;            // tile side
-constexpr int FWD4_MAX_F = 2048;  // 10 bytes of list per face -> <= 20 KB of dynamic shared memory
+constexpr int FWD4_CAP = 1536;    // tile-list entries held in shared memory (10 bytes each)
+constexpr int FWD4_MAX_F = 65535; // (any F: longer coarse lists take the windowed slow path)
 constexpr int WG4 = 16;           // list entries per warp group
 
-__host__ __device__ inline size_t fwd4_dyn_smem(int F) { return (size_t)F * 10 + 16; }
+__host__ __device__ inline size_t fwd4_dyn_smem(int F) { return (size_t)(F < FWD4_CAP ? F : FWD4_CAP) * 10 + 16; }
 
 template <int RGB>
 __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
@@ -31,9 +33,10 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict_
                                                         int ncb) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int F = K.F;
-    uint32_t* s_boff = reinterpret_cast<uint32_t*>(smem_dyn);                 // [F + 1]
-    uint32_t* s_meet = s_boff + (F + 1);                                      // [F]  bit q: rectangle meets pixel block q
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_meet + F);               // [F]
+    const int LC = F < FWD4_CAP ? F : FWD4_CAP;                               // list capacity
+    uint32_t* s_boff = reinterpret_cast<uint32_t*>(smem_dyn);                 // [LC + 1]
+    uint32_t* s_meet = s_boff + (LC + 1);                                     // [LC]  bit q: rectangle meets pixel block q
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_meet + LC);              // [LC]
     __shared__ __align__(128) float s_wrec[NWARP * 2 * WG4 * REC_F];          // 32 KB: warp-private record stages
     __shared__ float s_xp[T4], s_yp[T4], s_ext[4];
     __shared__ int s_warp_cnt[NWARP];
@@ -139,135 +142,80 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict_
     const float ext0 = s_ext[0], ext1 = s_ext[1], ext2 = s_ext[2], ext3 = s_ext[3];
     const uint32_t lt = (1u << lane) - 1u;
 
-    // ---- tile list: ordered compaction of the coarse entries that touch the tile, CTA entries per round ----------
-    int n = 0;
-    for (int r0 = 0; r0 < nc; r0 += CTA) {
-        const int i = r0 + tid;
-        bool hit = false;
-        uint32_t meet = 0;
-        uint16_t f = 0;
-        if (i < nc) {
-            f = __ldg(cl + i);
-            const float4 bb = __ldg(box + f);
-            hit = !(ext0 > bb.y || ext1 < bb.x || ext2 > bb.w || ext3 < bb.z);
-            if (hit) {
-                // 8-column bands / 4-row bands holding a pixel that passes the per-pixel cull test (kernel.cu:32-38);
-                // same comparisons, so a NaN box stays "never culled"
-                uint32_t cm = 0, rm = 0;
-#pragma unroll 8
-                for (int q = 0; q < T4; ++q) {
-                    const float x = s_xp[q], y = s_yp[q];
-                    if (q < ncol && !(x > bb.y || x < bb.x)) cm |= 1u << (q >> 3);
-                    if (q < nrow && !(y > bb.w || y < bb.z)) rm |= 1u << (q >> 2);
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if ((rm >> r) & 1u) meet |= cm << (4 * r);  // block q = r * 4 + c
-            }
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int off = n, tot = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) {
-            const int c = s_warp_cnt[w];
-            if (w < warp) off += c;
-            tot += c;
-        }
-        if (hit) {
-            const int pos = off + __popc(m & lt);
-            s_list[pos] = f;
-            s_meet[pos] = meet;
-        }
-        n += tot;
-        __syncthreads();  // entries visible; s_warp_cnt reusable
-    }
-
-    // ---- block offsets: exclusive prefix of popc(meet) over the list ------------------------------------------
-    {
-        uint32_t running = 0;
-        for (int r0 = 0; r0 < n; r0 += CTA) {
+    // ---- tile list: ordered compaction of the coarse entries [w0, w0 + nwin) that touch the tile (cooperative) -------
+    auto build_list = [&](int w0, int nwin) -> int {
+        int n = 0;
+        for (int r0 = 0; r0 < nwin; r0 += CTA) {
             const int i = r0 + tid;
-            const uint32_t v = i < n ? (uint32_t)__popc(s_meet[i]) : 0u;
-            uint32_t incl = v;
+            bool hit = false;
+            uint32_t meet = 0;
+            uint16_t f = 0;
+            if (i < nwin) {
+                f = __ldg(cl + w0 + i);
+                const float4 bb = __ldg(box + f);
+                hit = !(ext0 > bb.y || ext1 < bb.x || ext2 > bb.w || ext3 < bb.z);
+                if (hit) {
+                    // 8-column bands / 4-row bands holding a pixel that passes the per-pixel cull test (kernel.cu:32-38);
+                    // same comparisons, so a NaN box stays "never culled"
+                    uint32_t cm = 0, rm = 0;
+#pragma unroll 8
+                    for (int q = 0; q < T4; ++q) {
+                        const float x = s_xp[q], y = s_yp[q];
+                        if (q < ncol && !(x > bb.y || x < bb.x)) cm |= 1u << (q >> 3);
+                        if (q < nrow && !(y > bb.w || y < bb.z)) rm |= 1u << (q >> 2);
+                    }
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
+                    for (int r = 0; r < 8; ++r)
+                        if ((rm >> r) & 1u) meet |= cm << (4 * r);  // block q = r * 4 + c
+                }
             }
-            if (lane == 31) s_warp_blk[warp] = incl;
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_warp_cnt[warp] = __popc(m);
             __syncthreads();
-            uint32_t base = running, total = 0;
+            int off = n, tot = 0;
 #pragma unroll
             for (int w = 0; w < NWARP; ++w) {
-                const uint32_t c = s_warp_blk[w];
-                base += (w < warp) ? c : 0u;
-                total += c;
+                const int c = s_warp_cnt[w];
+                if (w < warp) off += c;
+                tot += c;
             }
-            if (i < n) s_boff[i] = base + incl - v;
-            running += total;
-            __syncthreads();  // s_warp_blk reusable
-        }
-        if (tid == 0) s_boff[n] = running;
-    }
-    __syncthreads();
-    const uint32_t NBw = n > 0 ? s_boff[n] : 0u;
-
-    // ---- reserve the tile's blocks in the pair buffer (one segment per tile) -----------------------------------
-    if (tid == 0) {
-        int32_t head = TILE_EMPTY;
-        if (s_save && NBw > 0) {
-            const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
-            if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
-                s_save = 0;  // does not fit: the tile falls back to the recompute backward (its four 16x16 tiles)
-                head = TILE_UNSAVED;
-                const int t16x = (S + TILE - 1) / TILE, t16y = t16x;
-                for (int dy = 0; dy < 2; ++dy)
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const int bx = blockIdx.x * 2 + dx, by = blockIdx.y * 2 + dy;
-                        if (bx < t16x && by < t16y) pb.ulist[atomicAdd(pb.ctrl + 1, 1u)] = (int32_t)(((size_t)b * t16y + by) * t16x + bx);
-                    }
-            } else {
-                pb.blk_hdr[base] = NBw;
-                pb.blk_hdr[base + 1] = SEG_NONE;
-                head = (int32_t)base;
-                s_segbase = base + 2u;
+            if (hit) {
+                const int pos = off + __popc(m & lt);
+                s_list[pos] = f;
+                s_meet[pos] = meet;
             }
+            n += tot;
+            __syncthreads();  // entries visible; s_warp_cnt reusable
         }
-        if (pb.cap > 0) pb.tile_head[tile_id] = head;
-    }
-    __syncthreads();  // s_save / s_segbase visible
-    const bool save = s_save != 0 && NBw > 0;
-    const uint32_t segbase = s_segbase;
+        return n;
+    };
+    const bool slow = nc > LC;  // uniform: the bin's list does not fit the shared tile list -> windowed static path below
     float* wst = s_wrec + warp * (2 * WG4 * REC_F);
-    const int ngroup = (n + WG4 - 1) / WG4;
     const float gstep = 2.f / (float)(S - 1);
 
-    // ---- warps grab 8x4 pixel blocks until the tile is done: no CTA barrier below this line ---------------------
-    for (;;) {
-        int q = 0;
-        if (lane == 0) q = atomicAdd(&s_next, 1);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= (T4 / 8) * (T4 / 4)) break;
+    struct PixelState { float acc_a, ssum, smax, c0, c1, c2, zmin; int fid; };
+    auto init_state = [&](PixelState& st) {  // kernel.cu:335-348
+        st.acc_a = 1.f; st.ssum = ssum0; st.smax = eps;
+        if (RGB == 1) { st.c0 = bg0 * ssum0; st.c1 = bg1 * ssum0; st.c2 = bg2 * ssum0; }
+        else { st.c0 = bg0; st.c1 = bg1; st.c2 = bg2; }
+        st.zmin = 10000000.f; st.fid = -1;
+    };
+
+    // ---- one pixel block (8x4, block q of the tile) against the n list entries currently in shared memory: the warp walks
+    // the entries in groups of WG4, stages the records of the faces meeting ITS block into its private cp.async double
+    // buffer and aggregates them in ascending face order.  No CTA barrier inside.
+    auto run_groups = [&](int q, int n, bool save, uint32_t segbase, PixelState& st) {
         const uint32_t qbit = 1u << q, qlow = qbit - 1u;
         const int lcol = (q & 3) * 8 + (lane & 7), lrow = (q >> 2) * 4 + (lane >> 3);
         const int px = tx0 + lcol, py = ty0 + lrow;
         const bool live = px < S && py < S;
         const float xp = s_xp[lcol], yp = s_yp[lrow];
-        // pixel state (kernel.cu:335-348)
-        float acc_a = 1.f;
-        float ssum = ssum0;
-        float smax = eps;
-        float c0, c1, c2;
-        if (RGB == 1) { c0 = bg0 * ssum; c1 = bg1 * ssum; c2 = bg2 * ssum; }
-        else { c0 = bg0; c1 = bg1; c2 = bg2; }
-        float zmin = 10000000.f;
-        int fid = -1;
         // torch-1.1 affine_grid (align_corners=True) coordinates of this pixel: linspace(-1, 1, S)
         const float gx = (px * 2 < S) ? (-1.f + gstep * px) : (1.f - gstep * (S - 1 - px));
         const float gy = (py * 2 < S) ? (-1.f + gstep * py) : (1.f - gstep * (S - 1 - py));
-
+        float acc_a = st.acc_a, ssum = st.ssum, smax = st.smax, c0 = st.c0, c1 = st.c1, c2 = st.c2, zmin = st.zmin;
+        int fid = st.fid;
+        const int ngroup = (n + WG4 - 1) / WG4;
         auto issue = [&](int g) -> uint32_t {
             uint32_t m = 0;
             if (g < ngroup) {
@@ -283,7 +231,6 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict_
             cp_async_commit();
             return m;
         };
-        // skip leading groups without a face for this block (cheap: one ballot each)
         uint32_t m_cur = issue(0);
         for (int g = 0; g < ngroup; ++g) {
             const uint32_t m_next = issue(g + 1);
@@ -384,20 +331,26 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict_
             __syncwarp();  // every lane is done with stage g & 1 before issue(g + 2) overwrites it
             m_cur = m_next;
         }
-        cp_async_wait<0>();  // (the trailing empty group) -- the stages are reused by the next block
+        cp_async_wait<0>();  // (the trailing empty group) -- the stages are reused by the next block / window
         __syncwarp();
+        st.acc_a = acc_a; st.ssum = ssum; st.smax = smax; st.c0 = c0; st.c1 = c1; st.c2 = c2; st.zmin = zmin; st.fid = fid;
+    };
 
-        // ---- finalise (kernel.cu:443-475), fused 2x2 pool, stores of this 8x4 block ---------------------------
-        const float alpha = (float)(1. - (double)acc_a);  // kernel.cu:449-451
+    // ---- finalise (kernel.cu:443-475), fused 2x2 pool, stores of one 8x4 block ---------------------------------
+    auto store_block = [&](int q, const PixelState& st) {
+        const int lcol = (q & 3) * 8 + (lane & 7), lrow = (q >> 2) * 4 + (lane >> 3);
+        const int px = tx0 + lcol, py = ty0 + lrow;
+        const bool live = px < S && py < S;
+        const float alpha = (float)(1. - (double)st.acc_a);  // kernel.cu:449-451
         float o0, o1, o2, g0, g1;
         if (RGB == 0) {
-            o0 = c0; o1 = c1; o2 = c2;
-            g0 = zmin; g1 = (float)fid;
+            o0 = st.c0; o1 = st.c1; o2 = st.c2;
+            g0 = st.zmin; g1 = (float)st.fid;
         } else {
-            o0 = c0 == 0.f ? c0 : c0 / ssum;
-            o1 = c1 == 0.f ? c1 : c1 / ssum;
-            o2 = c2 == 0.f ? c2 : c2 / ssum;
-            g0 = ssum; g1 = smax;
+            o0 = st.c0 == 0.f ? st.c0 : st.c0 / st.ssum;
+            o1 = st.c1 == 0.f ? st.c1 : st.c1 / st.ssum;
+            o2 = st.c2 == 0.f ? st.c2 : st.c2 / st.ssum;
+            g0 = st.ssum; g1 = st.smax;
         }
         float v[4] = {o0, o1, o2, alpha};
         if (K.aa) {
@@ -434,6 +387,98 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict_
                 images[((size_t)b * 4 + 3) * np + p] = alpha;
             }
         }
+    };
+    // the tile's four 16x16 tiles go to the recompute backward
+    auto mark_unsaved = [&]() {
+        const int t16x = (S + TILE - 1) / TILE, t16y = t16x;
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                const int bx = blockIdx.x * 2 + dx, by = blockIdx.y * 2 + dy;
+                if (bx < t16x && by < t16y) pb.ulist[atomicAdd(pb.ctrl + 1, 1u)] = (int32_t)(((size_t)b * t16y + by) * t16x + bx);
+            }
+    };
+
+    if (slow) {
+        // ---- SLOW path (coarse list longer than the shared tile list): windows of LC entries, static block assignment
+        // (pass p: warp w owns block p * 8 + w, its pixel state lives in registers across the windows), no record saving
+        if (tid == 0 && pb.cap > 0) { pb.tile_head[tile_id] = TILE_UNSAVED; mark_unsaved(); }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int q = pass * NWARP + warp;
+            PixelState st;
+            init_state(st);
+            for (int w0 = 0; w0 < nc; w0 += LC) {
+                const int n = build_list(w0, min(LC, nc - w0));
+                run_groups(q, n, false, 0u, st);
+                __syncthreads();  // every warp is done with this window's list before it is rebuilt
+            }
+            store_block(q, st);
+        }
+        return;
+    }
+
+    const int n = build_list(0, nc);
+    // ---- block offsets: exclusive prefix of popc(meet) over the list ------------------------------------------
+    {
+        uint32_t running = 0;
+        for (int r0 = 0; r0 < n; r0 += CTA) {
+            const int i = r0 + tid;
+            const uint32_t v = i < n ? (uint32_t)__popc(s_meet[i]) : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) s_warp_blk[warp] = incl;
+            __syncthreads();
+            uint32_t base = running, total = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) {
+                const uint32_t c = s_warp_blk[w];
+                base += (w < warp) ? c : 0u;
+                total += c;
+            }
+            if (i < n) s_boff[i] = base + incl - v;
+            running += total;
+            __syncthreads();  // s_warp_blk reusable
+        }
+        if (tid == 0) s_boff[n] = running;
+    }
+    __syncthreads();
+    const uint32_t NBw = s_boff[n];
+
+    // ---- reserve the tile's blocks in the pair buffer (one segment per tile) -----------------------------------
+    if (tid == 0) {
+        int32_t head = TILE_EMPTY;
+        if (s_save && NBw > 0) {
+            const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
+            if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
+                s_save = 0;  // does not fit: the tile falls back to the recompute backward
+                head = TILE_UNSAVED;
+                mark_unsaved();
+            } else {
+                pb.blk_hdr[base] = NBw;
+                pb.blk_hdr[base + 1] = SEG_NONE;
+                head = (int32_t)base;
+                s_segbase = base + 2u;
+            }
+        }
+        if (pb.cap > 0) pb.tile_head[tile_id] = head;
+    }
+    __syncthreads();  // s_save / s_segbase visible
+    const bool save = s_save != 0 && NBw > 0;
+    const uint32_t segbase = s_segbase;
+
+    // ---- warps grab 8x4 pixel blocks until the tile is done: no CTA barrier below this line ---------------------
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&s_next, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= (T4 / 8) * (T4 / 4)) break;
+        PixelState st;
+        init_state(st);
+        run_groups(q, n, save, segbase, st);
+        store_block(q, st);
     }
 }
 

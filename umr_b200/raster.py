@@ -89,6 +89,7 @@ def collect_profile(sink):
 # Budget in candidate pairs per raster pixel (measured: 2.7 at F=1280, 4.8 at F=5120) and an
 # upper bound on one render's buffer; tiles that do not fit are recomputed by the backward (same results).
 PAIR_CAND_PER_PIXEL = float(os.environ.get("UMR_PAIR_CAND_PER_PIXEL", "8.0"))
+FORWARD_TILE = int(os.environ.get("UMR_FORWARD_TILE", "0"))  # 0 auto | 16 | 32 (UmrRasterParams.tile_mode; tests force both)
 PAIR_MAX_BYTES = int(float(os.environ.get("UMR_PAIR_MAX_GB", "24")) * (1 << 30))
 
 
@@ -159,6 +160,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
                              eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb,
                              aggr_func_alpha, texture_type)
         params.shared_textures = group if group > 1 else 0
+        params.tile_mode = FORWARD_TILE
         need_bwd = face_vertices.requires_grad or textures.requires_grad
         _attach_events(params, "fwd")
         with torch.cuda.device(dev):
