@@ -15,7 +15,9 @@ from umr_b200.nnutils import chamfer_python, geom_utils, loss_utils, smr
 
 def main():
     dev = torch.device("cuda:0")
-    rng = np.random.default_rng(0)
+    seed = int(os.environ.get("SEED", "0"))
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
     v, f = synth.icosphere(2)
     B, IS = 2, 24
     verts = torch.from_numpy(synth.bird_like(v, rng, B)).to(dev).requires_grad_(True)
@@ -42,6 +44,31 @@ def main():
     o2, _, _ = raster.soft_rasterize(fv, vt, IS, dist_func="barycentric", aggr_func_alpha="sum", texture_type="vertex",
                                      sigma_val=1e-4, dist_eps=1e-4, gamma_val=1e-3, anti_aliasing=True)
     total = total + o2.mean()
+    # round-2 kernels: fused loss head, camera-hypothesis broadcast (vertex + raster kernels, shared textures),
+    # the 32x32-tile forward + its streamed backward, mesh regularisers, distance transform, texture atlas
+    from umr_b200 import ops
+    from umr_b200 import soft_renderer as sr
+    r2 = smr.SoftRenderer(IS, "softmax")
+    r2.ambient_light_only()
+    H = 4
+    cams_h = torch.from_numpy(np.stack([synth.cameras(rng, H) for _ in range(B)])).view(-1, 7).to(dev)
+    img_h, _, _ = r2(verts, faces, cams_h, tex)                      # [B*H] renders of B meshes / textures
+    gt_h = imgs.repeat_interleave(H, 0)
+    total = total + loss_utils.mask_texture_loss(img_h, gt_h, masks.repeat_interleave(H, 0), 2.5, 3.0)
+    old_tile = raster.FORWARD_TILE
+    raster.FORWARD_TILE = 32
+    try:
+        img32, _, _ = r2(verts, faces, cams, tex[:1])               # one batch-shared texture, 32x32-tile kernels
+        total = total + img32.mean()
+    finally:
+        raster.FORWARD_TILE = old_tile
+    fcpu = torch.from_numpy(f.astype(np.int64))
+    total = total + 1e-3 * sr.LaplacianLoss(torch.from_numpy(v), fcpu).to(dev)(verts).sum() \
+        + 1e-3 * sr.FlattenLoss(fcpu).to(dev)(verts).sum()
+    dtb = ops.dt_barrier(masks)
+    assert torch.isfinite(dtb).all()
+    atlas, _ = sr.functional.create_texture_image(tex[0].detach(), 8)
+    assert np.isfinite(atlas).all()
     total.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(verts.grad).all() and torch.isfinite(cams.grad).all() and torch.isfinite(flow.grad).all()

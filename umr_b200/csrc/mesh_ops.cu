@@ -299,19 +299,22 @@ __global__ void __launch_bounds__(256) k_edt_rows(const int32_t* __restrict__ g_
     for (int x = threadIdx.x; x < W; x += blockDim.x) { s_g[x] = go[x]; s_g[W + x] = gi[x]; }
     __syncthreads();
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
-        long long best_o = (long long)EDT_INF * EDT_INF, best_i = best_o;
+        // exact in 32 bits: dx^2 <= 4095^2 and g^2 <= 65535^2 would overflow, so columns are capped at W <= 4096 and
+        // column distances above 32767 cannot beat any finite candidate -- they are clamped to "infinite"
+        constexpr int NONE = 0x7fffffff;
+        int best_o = NONE, best_i = NONE;
+#pragma unroll 4
         for (int xp = 0; xp < W; ++xp) {
-            const long long dx2 = (long long)(x - xp) * (x - xp);
+            const int dx = x - xp, dx2 = dx * dx;
             const int a = s_g[xp], c = s_g[W + xp];
-            if (a < EDT_INF) best_o = min(best_o, dx2 + (long long)a * a);
-            if (c < EDT_INF) best_i = min(best_i, dx2 + (long long)c * c);
+            if (a < 32768) best_o = min(best_o, dx2 + a * a);
+            if (c < 32768) best_i = min(best_i, dx2 + c * c);
         }
-        // scipy returns float64 distances; the reference forms the sigmoid in float64 and casts to float32 (train_s2.py:196)
         // no feature pixel in the whole image (full / empty mask): scipy's distance_transform_edt then measures from a
         // virtual pixel at (row -1, column 0) -- reproduced so that degenerate masks match the reference too
-        const long long none = (long long)EDT_INF * EDT_INF, virt = (long long)(y + 1) * (y + 1) + (long long)x * x;
-        if (best_o == none) best_o = virt;
-        if (best_i == none) best_i = virt;
+        const int virt = (y + 1) * (y + 1) + x * x;
+        if (best_o == NONE) best_o = virt;
+        if (best_i == NONE) best_i = virt;
         const double d_out = sqrt((double)best_o), d_in = sqrt((double)best_i);
         const double diff = (d_out - d_in) * (double)inv_norm;
         dt[((size_t)b * H + y) * W + x] = (float)(1. / (1. + exp((double)k * -diff)));
@@ -402,7 +405,7 @@ extern "C" size_t umr_dt_barrier_workspace_bytes(int32_t B, int32_t H, int32_t W
 extern "C" int umr_dt_barrier(const float* mask, float* dt, void* workspace, int32_t B, int32_t H, int32_t W, float k,
                               void* stream_) {
     if (!mask || !dt || !workspace || B <= 0 || H <= 0 || W <= 0) return UMR_ERR_BAD_ARG;
-    if (B > 65535 || H > 65535 || W > 4096) return UMR_ERR_TOO_LARGE;
+    if (B > 65535 || H > 32767 || W > 4096) return UMR_ERR_TOO_LARGE;  // 32-bit exact squared distances (k_edt_rows)
     cudaStream_t st = (cudaStream_t)stream_;
     int32_t* g_out = (int32_t*)workspace;
     int32_t* g_in = g_out + (size_t)B * H * W;

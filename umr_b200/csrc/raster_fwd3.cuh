@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
         if (NBw == 0) continue;  // uniform: no rectangle holds a pixel
 
         // ---- reserve the segment's blocks in the pair buffer --------------------------------------------------
-        if (tid == 0 && s_save) {
+        if (tid == 0 && *reinterpret_cast<volatile int*>(&s_save)) {  // thread 0 only (volatile: the read is not hoisted)
             const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
             if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
                 s_save = 0;  // does not fit: the whole tile falls back to the recompute backward

@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_fwd4(const float* __restrict_
     // ---- reserve the tile's blocks in the pair buffer (one segment per tile) -----------------------------------
     if (tid == 0) {
         int32_t head = TILE_EMPTY;
-        if (s_save && NBw > 0) {
+        const int save_prev = *reinterpret_cast<volatile int*>(&s_save);  // read by thread 0 only (volatile: not hoisted)
+        if (save_prev && NBw > 0) {
             const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
             if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
                 s_save = 0;  // does not fit: the tile falls back to the recompute backward

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
         if (NBw == 0) continue;  // uniform: every rectangle is empty
 
         // ---- reserve the segment's blocks in the pair buffer --------------------------------------------------
-        if (tid == 0 && s_save) {
+        if (tid == 0 && *reinterpret_cast<volatile int*>(&s_save)) {  // thread 0 only (volatile: the read is not hoisted)
             const uint32_t base = atomicAdd(pb.ctrl, NBw + 2u);
             if ((uint64_t)base + NBw + 2u > (uint64_t)pb.cap) {
                 s_save = 0;  // does not fit: the whole tile falls back to the recompute backward
@@ -643,9 +643,15 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
 // ---------------------------------------------------------------------------------------------
 // backward: stream the saved pair records of the tile
 // ---------------------------------------------------------------------------------------------
+#ifndef UMR_BWD2_REGPIPE
+#define UMR_BWD2_REGPIPE 0
+#endif
+#ifndef UMR_BWD2_CTAS
+#define UMR_BWD2_CTAS 4
+#endif
 // TS: side of the forward's tile (16: k_raster_fwd3 / k_raster_fwd2, 32: k_raster_fwd4); one CTA streams one tile
 template <int RGB, bool TEXGRAD, int TS>
-__global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
+__global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                         const float* __restrict__ aggrs, const float* __restrict__ grad_images,
                                                         float* __restrict__ grad_faces, float* __restrict__ grad_tex, Consts K,
                                                         PairBuf pb) {
@@ -767,24 +773,37 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
             }
             return false;
         };
-        auto prefetch = [&](const float4* p) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
+        // The records of step i + 1 are LOADED INTO REGISTERS while step i is processed (12 registers; UMR_BWD2_REGPIPE=0
+        // falls back to an L1 prefetch hint): the loads' latency is then covered by a whole step of arithmetic.
+        auto load3 = [&](bool act, const float4* p, float4& a, float4& b_, float4& c) {
+#if UMR_BWD2_REGPIPE
+            if (act) { a = __ldg(p); b_ = __ldg(p + 32); c = __ldg(p + 64); }
+#else
+            if (act) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
+            }
+#endif
         };
         int f_c = 0, f_n = 0;
         bool act_c = false, act_n = false;
         const float4 *src_c = nullptr, *src_n = nullptr;
+        float4 c0r = make_float4(0, 0, 0, 0), c1r = c0r, c2r = c0r, n0r = c0r, n1r = c0r, n2r = c0r;
         bool have = plan(f_c, act_c, src_c);
-        if (have && act_c) prefetch(src_c);
+        if (have) load3(act_c, src_c, c0r, c1r, c2r);
         while (have) {
             const bool have_n = plan(f_n, act_n, src_n);
-            if (have_n && act_n) prefetch(src_n);
+            if (have_n) load3(act_n, src_n, n0r, n1r, n2r);
             const int f = f_c;
             if (f != cur_f) { flush(); cur_f = f; }
             if (act_c) {
+#if UMR_BWD2_REGPIPE
+                const float4 r0 = c0r, r1 = c1r, r2 = c2r;
+#else
                 const float4* src = src_c;
                 const float4 r0 = __ldg(src), r1 = __ldg(src + 32), r2 = __ldg(src + 64);
+#endif
                 const float D = r0.x, sdx = r0.y, sdy = r0.z, zn = r0.w;  // zn: normalised depth exactly as the forward formed it
                 const uint32_t meta = __float_as_uint(r1.w);
                 const int pix = TS == 16 ? (int)(meta & 0xffu) : (int)(meta & 0x3ffu);
@@ -842,6 +861,7 @@ __global__ void __launch_bounds__(CTA, 4) k_raster_bwd2(const float* __restrict_
                 acc[7] += q * r1.z * sdy;
             }
             f_c = f_n; act_c = act_n; src_c = src_n; have = have_n;
+            c0r = n0r; c1r = n1r; c2r = n2r;
         }
         seg = next;
     }
