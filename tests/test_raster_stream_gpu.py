@@ -14,9 +14,10 @@ DEV = "cuda:0"
 
 
 def _run(fv, tex, image_size, rgb, g, cand_per_pixel, tile=0):
-    old, old_tile = raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE
+    old, old_tile, old_ad = raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE, raster.PAIR_ADAPTIVE
     raster.PAIR_CAND_PER_PIXEL = cand_per_pixel
     raster.FORWARD_TILE = tile
+    raster.PAIR_ADAPTIVE = False   # fixed budgets here; the adaptive sizing has its own test below
     try:
         tfv = torch.from_numpy(fv).to(DEV).requires_grad_(True)
         ttex = torch.from_numpy(tex).to(DEV).requires_grad_(True)
@@ -30,7 +31,7 @@ def _run(fv, tex, image_size, rgb, g, cand_per_pixel, tile=0):
         return dict(images=img.detach().cpu().numpy(), grad_faces=tfv.grad.cpu().numpy(), grad_tex=ttex.grad.cpu().numpy(),
                     stats=stats)
     finally:
-        raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE = old, old_tile
+        raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE, raster.PAIR_ADAPTIVE = old, old_tile, old_ad
 
 
 @pytest.mark.parametrize("tile", [16, 32])   # k_raster_fwd3 (16x16, static warps) / k_raster_fwd4 (32x32, dynamic pixel blocks)
@@ -111,3 +112,36 @@ def test_dense_mesh_takes_the_windowed_slow_path(rgb):
     for got in (a, b):
         ok, msg = rel_report("grad_faces", got["grad_faces"], ref["grad_faces"], 1e-4, at)
         assert ok, msg
+
+
+def test_pair_buffer_sizing_adapts_to_the_measured_need(monkeypatch):
+    """The buffer's own counters are read back asynchronously; later renders of the same (raster size, face count) get a
+    buffer sized from the measured need instead of the fixed budget, and a render that outgrows it only recomputes tiles."""
+    monkeypatch.setattr(raster, "PAIR_ADAPTIVE", True)
+    monkeypatch.setattr(raster, "PAIR_CAND_PER_PIXEL", 32.0)
+    monkeypatch.setattr(raster, "FORWARD_TILE", 0)
+    raster._pair_need.clear()
+    del raster._pair_pending[:]
+    fv, tex = scene(2, 3, 2, seed=41)
+    g = torch.ones(2, 4, 64, 64, device=DEV)
+
+    def render(f):
+        tfv = torch.from_numpy(f).to(DEV).requires_grad_(True)
+        img, _, _ = raster.soft_rasterize(tfv, torch.from_numpy(tex).to(DEV), 64, anti_aliasing=True, **UMR)
+        pairs = img.grad_fn.saved_tensors[4]
+        img.backward(g)
+        torch.cuda.synchronize()
+        return pairs.numel(), pairs[:8].view(torch.int32).cpu().tolist(), tfv.grad.cpu().numpy()
+
+    n0, st0, g0 = render(fv)                  # fixed budget
+    n1, st1, g1 = render(fv)                  # sized from the first call's counters
+    assert st0[1] == 0 and st1[1] == 0
+    assert n1 < 0.5 * n0, (n0, n1)
+    assert (128, fv.shape[1], 0) in raster._pair_need
+    big = fv.copy()
+    big[..., [0, 1, 3, 4, 6, 7]] *= 1.6       # a much larger silhouette: outgrows the adapted buffer
+    n2, st2, g2 = render(big)
+    n3, st3, g3 = render(big)
+    assert st3[1] == 0 and n3 > n2 * 0.99     # grown after the overflow was observed
+    ok, msg = rel_report("grad (overflowing vs grown buffer)", g2, g3, 1e-4, 1e-6 * float(np.abs(g3).max()) + 1e-7)
+    assert ok, msg

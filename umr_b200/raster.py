@@ -93,14 +93,49 @@ FORWARD_TILE = int(os.environ.get("UMR_FORWARD_TILE", "0"))  # 0 auto | 16 | 32 
 PAIR_MAX_BYTES = int(float(os.environ.get("UMR_PAIR_MAX_GB", "24")) * (1 << 30))
 
 
-def pair_buffer_bytes(B, image_size, anti_aliasing, cand_per_pixel=None):
+def pair_buffer_bytes(B, image_size, anti_aliasing, cand_per_pixel=None, blocks_per_image=None):
     lib = _lib.load()
     S = int(image_size) * (2 if anti_aliasing else 1)
     cpp = PAIR_CAND_PER_PIXEL if cand_per_pixel is None else cand_per_pixel
     tiles = B * ((S + 15) // 16) ** 2
-    blocks = int(B * S * S * cpp / 32.0) + 2 * tiles + 64
+    if blocks_per_image is not None:
+        blocks = int(B * blocks_per_image * PAIR_HEADROOM) + 2 * tiles + 64
+    else:
+        blocks = int(B * S * S * cpp / 32.0) + 2 * tiles + 64
     nbytes = lib.umr_raster_pair_buffer_bytes(B, int(image_size), 1 if anti_aliasing else 0, blocks)
     return min(int(nbytes), PAIR_MAX_BYTES)
+
+
+# Adaptive sizing: after every forward the buffer's own counters (blocks the render WANTED, tiles left unsaved) are copied
+# to pinned memory asynchronously; a later call with the same (raster size, face count) sizes its buffer from the largest
+# need seen per image (x PAIR_HEADROOM) instead of the fixed budget -- 0.8 GB instead of 1.7 GB at C2.  A render that
+# needs more than that just recomputes some tiles in its backward (same results) and the next one grows.  Nothing here
+# synchronises; inside CUDA-graph capture the read-back is skipped.
+PAIR_HEADROOM = float(os.environ.get("UMR_PAIR_HEADROOM", "1.35"))
+PAIR_ADAPTIVE = os.environ.get("UMR_PAIR_ADAPTIVE", "1") != "0"
+_pair_need = {}      # (S, F, tile_mode) -> blocks per image
+_pair_pending = []   # (key, B, pinned int32[2], event)
+
+
+def _pair_poll():
+    keep = []
+    for key, B, host, ev in _pair_pending:
+        if ev.query():
+            need = float(host[0]) / max(B, 1)
+            _pair_need[key] = max(_pair_need.get(key, 0.0), need)
+        else:
+            keep.append((key, B, host, ev))
+    _pair_pending[:] = keep
+
+
+def _pair_record(key, B, pairs):
+    if not PAIR_ADAPTIVE or torch.cuda.is_current_stream_capturing() or len(_pair_pending) > 64:
+        return
+    host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+    host.copy_(pairs[:8].view(torch.int32), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pair_pending.append((key, B, host, ev))
 
 
 def _stream_ptr(device):
@@ -175,14 +210,22 @@ class SoftRasterizeFunction(torch.autograd.Function):
                              dtype=torch.uint8)
             pairs = None
             generic = dist_func != "euclidean" or aggr_func_alpha != "prod" or texture_type != "surface"
+            pair_key = (S, F, FORWARD_TILE)
             if need_bwd and not generic and PAIR_CAND_PER_PIXEL > 0:
-                pairs = torch.empty(pair_buffer_bytes(B, image_size, anti_aliasing), device=dev, dtype=torch.uint8)
+                capturing = torch.cuda.is_current_stream_capturing()
+                if PAIR_ADAPTIVE and not capturing:
+                    _pair_poll()
+                need = _pair_need.get(pair_key) if (PAIR_ADAPTIVE and PAIR_CAND_PER_PIXEL >= 1.0) else None
+                pairs = torch.empty(pair_buffer_bytes(B, image_size, anti_aliasing, blocks_per_image=need), device=dev,
+                                    dtype=torch.uint8)
                 params.pair_buffer, params.pair_buffer_bytes = pairs.data_ptr(), pairs.numel()
             rc = lib.umr_raster_forward(_ptr(fv), _ptr(tex), _ptr(images),
                                         _ptr(colors_hi) if anti_aliasing else _ptr(None),
                                         _ptr(aggrs), _ptr(p2f), ctypes.byref(params), _ptr(ws),
                                         _stream_ptr(dev))
         _lib.check(rc, "umr_raster_forward")
+        if pairs is not None:
+            _pair_record(pair_key, B, pairs)
         params.ev_kernel_start = params.ev_kernel_stop = None
         ctx.params = params
         ctx.in_shape = tuple(face_vertices.shape)
