@@ -78,6 +78,13 @@ typedef struct UmrRasterParams {
     /* forward tiling: 0 = automatic (by grid size), 16 = 16x16 tiles with one warp per 8x4 pixel block, 32 = 32x32 tiles
      * whose warps grab pixel blocks dynamically (F <= 2048).  Must be the same in the matching backward call. */
     int32_t tile_mode;
+    /* colour channels C of `textures` [..,F,T2,C]: 0 or 3 = RGB.  4 = the part-map render of part_matching_loss
+     * (loss_utils.py:385-399 renders its four one-hot part maps as four 3-identical-channel images; colour channels
+     * never interact in the rasteriser, so ONE render with C = 4 carries all of them): images / soft_colors /
+     * grad_images are then [B,5,..] = (c0..c3, alpha), the 4th background value is `background_extra`.  C = 4 is built
+     * for UMR's own configuration only (euclidean / softmax / prod, surface textures, no texture gradient). */
+    int32_t color_channels;
+    float background_extra;
 } UmrRasterParams;
 
 const char* umr_error_string(int code);
@@ -102,7 +109,7 @@ size_t umr_raster_pair_buffer_bytes(int32_t batch_size, int32_t image_size, int3
 
 /* Forward.  face_vertices [B,F,9] f32 (x0,y0,z0,x1,...), textures [B,F,T2,3] f32.
  * Outputs (all fully written, no pre-fill needed):
- *   images      [B,4,is,is]   pooled RGBA (== soft_colors when anti_aliasing == 0)
+ *   images      [B,4,is,is]   pooled RGBA (== soft_colors when anti_aliasing == 0); [B,5,..] with color_channels == 4
  *   soft_colors [B,4,S,S]     un-pooled RGBA, needed by backward; may be NULL when anti_aliasing==0
  *                             (images is then the un-pooled tensor) or when no backward will follow
  *   aggrs_info  [B,2,S,S]     softmax: (sum, max); hard: (depth_min, float(face_index_min))
@@ -113,7 +120,9 @@ int umr_raster_forward(const float* face_vertices, const float* textures, float*
 
 /* Backward.  grad_images [B,4,is,is] is the gradient w.r.t. `images` (the 2x2 pool backward is
  * fused).  Outputs are zero-filled by the call, then accumulated:
- *   grad_faces    [B,F,9]
+ *   grad_faces    [B,F,9]     may be NULL when grad_textures is given: texture-only backward for renders of DETACHED
+ *                             geometry (UMR's texture branch, experiments/train_s2.py:248) -- the vertex-gradient
+ *                             arithmetic is compiled out (euclidean / prod / surface configuration only)
  *   grad_textures [B,F,T2,3]  may be NULL (skips the texture gradient, e.g. silhouette renders)
  * Only the sampled texel receives texture gradient (intended semantics of kernel.cu:199-218; the
  * reference's uninitialised-variable behaviour is NOT reproduced -- SURVEY.md App. B-1). */

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported():
 
 def test_scalar_entry_points_without_gpu():
     lib = _lib.load()
-    assert lib.umr_version() >= 200
+    assert lib.umr_version() >= 201
     assert lib.umr_error_string(0) == b"ok"
     assert b"not supported" in lib.umr_error_string(-1)
     assert lib.umr_raster_workspace_bytes(16, 1280, 256, 1) >= 16 * 1280 * (128 + 16 + 16) + 16 * 64 * 1280 * 2
@@ -41,7 +41,8 @@ def test_scalar_entry_points_without_gpu():
 
 def test_params_struct_matches_header():
     p = _lib.UmrRasterParams()
-    assert ctypes.sizeof(p) == 5 * 4 + 6 * 4 + 5 * 4 + 3 * 4 + 4 + 2 * 8 + 8 + 8 + 8  # 4 bytes padding before the pointers
+    # 4 bytes padding before the pointers; shared_textures, tile_mode, color_channels, background_extra = 16
+    assert ctypes.sizeof(p) == 5 * 4 + 6 * 4 + 5 * 4 + 3 * 4 + 4 + 2 * 8 + 8 + 8 + 16
     lib = _lib.load()
     assert lib.umr_sizeof_raster_params() == ctypes.sizeof(p)
     assert lib.umr_sizeof_project_params() == ctypes.sizeof(_lib.UmrProjectParams())

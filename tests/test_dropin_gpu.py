@@ -162,8 +162,9 @@ def test_fused_vertex_pipeline_matches_torch_glue(ambient_only, with_tex):
 
 
 def test_part_matching_loss_packed_renders_match_reference_pattern():
-    """part_matching_loss (loss_utils.py:333-440): the 2 packed renders give the same projections as the
-    reference's 4 separate one-hot renders; loss and gradients agree."""
+    """part_matching_loss (loss_utils.py:333-440): ONE 4-colour-channel render gives the same
+    projections as the reference's 4 separate one-hot renders; loss and gradients agree."""
+    from umr_b200 import raster
     B, IS, T = 2, 32, 2
     rng = np.random.default_rng(11)
     v, f = synth.icosphere(2)
@@ -180,8 +181,15 @@ def test_part_matching_loss_packed_renders_match_reference_pattern():
         m = loss_utils.part_matching_loss(None, None, 0, im_size=IS, batch_size=B, tex_size=T, stex_one_hot=one_hot).to(DEV)
         m.pack_parts = pack
         vv = verts0.clone().to(DEV).requires_grad_(True)
-        loss, projs = m(vv, faces, cams, part_segs)
-        loss.backward()
+        sink = []
+        raster.set_profile_sink(sink)
+        try:
+            loss, projs = m(vv, faces, cams, part_segs)
+            loss.backward()
+        finally:
+            raster.set_profile_sink(None)
+        kinds = [k for k, _ in sink]
+        assert kinds.count("fwd") == (1 if pack else 4) and kinds.count("bwd") == (1 if pack else 4), kinds
         outs.append((loss.item(), [p.detach().cpu() for p in projs], vv.grad.cpu()))
     for pa, pb in zip(outs[0][1], outs[1][1]):
         assert torch.equal(pa, pb)

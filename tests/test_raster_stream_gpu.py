@@ -145,3 +145,77 @@ def test_pair_buffer_sizing_adapts_to_the_measured_need(monkeypatch):
     assert st3[1] == 0 and n3 > n2 * 0.99     # grown after the overflow was observed
     ok, msg = rel_report("grad (overflowing vs grown buffer)", g2, g3, 1e-4, 1e-6 * float(np.abs(g3).max()) + 1e-7)
     assert ok, msg
+
+
+@pytest.mark.parametrize("cand", [32.0, 0.7, 0.0])   # all pairs saved / some tiles recomputed / no pair buffer at all
+@pytest.mark.parametrize("B,subdiv,tex_res,image_size,aa", [(2, 3, 3, 64, True), (1, 2, 2, 37, True), (2, 2, 2, 48, False)])
+def test_four_colour_channels_equal_two_rgb_renders(cand, B, subdiv, tex_res, image_size, aa):
+    """textures [B,F,T2,4] render all four part maps of part_matching_loss (loss_utils.py:385-399)
+    in ONE launch.  Colour channels never interact in the rasteriser, so planes 0-3 must be BIT-identical to the
+    same channels rendered through the 3-channel kernels, alpha identical, and the vertex gradient equal to the sum
+    of the two 3-channel renders' gradients (each checked against the CPU oracle elsewhere)."""
+    fv, tex3 = scene(B, subdiv, tex_res, seed=77 + image_size)
+    rng = np.random.default_rng(9)
+    extra = rng.uniform(0, 1, size=tex3.shape[:3] + (1,)).astype(np.float32)
+    tex4 = np.concatenate([tex3, extra], axis=-1)
+    texb = np.concatenate([extra, np.zeros_like(tex3[..., :2])], axis=-1)   # 4th channel rides in R of a second render
+    g = rng.normal(size=(B, 5, image_size, image_size)).astype(np.float32)
+    old, old_ad = raster.PAIR_CAND_PER_PIXEL, raster.PAIR_ADAPTIVE
+    raster.PAIR_CAND_PER_PIXEL, raster.PAIR_ADAPTIVE = cand, False
+    try:
+        def render(tex, gimg):
+            tfv = torch.from_numpy(fv).to(DEV).requires_grad_(True)
+            img, p2f, aggr = raster.soft_rasterize(tfv, torch.from_numpy(tex).to(DEV), image_size, aggr_func_rgb="softmax",
+                                                   anti_aliasing=aa, **UMR)
+            img.backward(torch.from_numpy(gimg).to(DEV))
+            return img.detach().cpu().numpy(), p2f.cpu().numpy(), aggr.cpu().numpy(), tfv.grad.cpu().numpy()
+        i4, p4, a4, gf4 = render(tex4, g)
+        ga = np.ascontiguousarray(g[:, [0, 1, 2, 4]])                       # RGB + alpha gradient
+        gb = np.zeros_like(ga); gb[:, 0] = g[:, 3]                          # 4th channel, no alpha gradient (counted once)
+        ia, pa, aa_, gfa = render(tex3, ga)
+        ib, _, _, gfb = render(texb, gb)
+    finally:
+        raster.PAIR_CAND_PER_PIXEL, raster.PAIR_ADAPTIVE = old, old_ad
+    assert i4.shape == (B, 5, image_size, image_size)
+    assert np.array_equal(i4[:, 0:3], ia[:, 0:3]) and np.array_equal(i4[:, 3], ib[:, 0]) and np.array_equal(i4[:, 4], ia[:, 3])
+    assert np.array_equal(a4, aa_)
+    np.testing.assert_allclose(p4, pa, rtol=1e-5, atol=1e-6)   # p2f sums are float REDs: order varies run to run
+    want = gfa + gfb
+    ok, msg = rel_report("grad_faces 4ch", gf4, want, 2e-4, 2e-6 * float(np.abs(want).max()) + 1e-7)
+    print(msg)
+    assert ok, msg
+
+
+def test_four_channel_mode_rejects_what_it_was_not_built_for():
+    fv, tex3 = scene(1, 2, 2, seed=1)
+    tex4 = np.concatenate([tex3, tex3[..., :1]], axis=-1)
+    tfv = torch.from_numpy(fv).to(DEV).requires_grad_(True)
+    with pytest.raises(ValueError):   # texture gradient
+        raster.soft_rasterize(tfv, torch.from_numpy(tex4).to(DEV).requires_grad_(True), 32, anti_aliasing=True, **UMR)
+    with pytest.raises(Exception):    # hard colour aggregation: UMR_ERR_UNSUPPORTED from the library
+        raster.soft_rasterize(tfv, torch.from_numpy(tex4).to(DEV), 32, aggr_func_rgb="hard", anti_aliasing=True, **UMR)
+
+
+@pytest.mark.parametrize("tile", [16, 32])
+@pytest.mark.parametrize("rgb", ["softmax", "hard"])
+@pytest.mark.parametrize("cand", [32.0, 0.7])
+def test_texture_only_backward_for_detached_geometry(tile, rgb, cand):
+    """UMR's texture branch renders DETACHED vertices / cameras (experiments/train_s2.py:248): the backward then forms
+    only the texel gradients (k_raster_bwd2<..., GEOM = false>) -- same values as the full backward, no grad_faces."""
+    B, image_size = 2, 64
+    fv, tex = scene(B, 3, 3, seed=5)
+    g = np.random.default_rng(6).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
+    full = _run(fv, tex, image_size, rgb, g, cand, tile)
+    old, old_tile, old_ad = raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE, raster.PAIR_ADAPTIVE
+    raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE, raster.PAIR_ADAPTIVE = cand, tile, False
+    try:
+        tfv = torch.from_numpy(fv).to(DEV)                       # no grad
+        ttex = torch.from_numpy(tex).to(DEV).requires_grad_(True)
+        img, _, _ = raster.soft_rasterize(tfv, ttex, image_size, aggr_func_rgb=rgb, anti_aliasing=True, **UMR)
+        img.backward(torch.from_numpy(g).to(DEV))
+    finally:
+        raster.PAIR_CAND_PER_PIXEL, raster.FORWARD_TILE, raster.PAIR_ADAPTIVE = old, old_tile, old_ad
+    assert np.array_equal(img.detach().cpu().numpy(), full["images"])
+    ok, msg = rel_report("grad_tex (texture-only)", ttex.grad.cpu().numpy(), full["grad_tex"], 1e-5, 1e-7)
+    print(msg)
+    assert ok, msg

@@ -62,6 +62,14 @@ def main():
         total = total + img32.mean()
     finally:
         raster.FORWARD_TILE = old_tile
+    # 4-colour-channel part-map render (one batch-shared texture) + texture-only backward for detached geometry
+    parts = torch.rand(1, f.shape[0], 4, 4, device=dev)
+    img4, _, _ = r2(verts, faces, cams, parts)
+    assert img4.shape[1] == 5
+    total = total + img4[:, :4].mean()
+    tex_leaf = tex.detach().clone().requires_grad_(True)
+    img_t, _, _ = r2(verts.detach(), faces, cams.detach(), tex_leaf)
+    total = total + img_t[:, :3].mean()
     fcpu = torch.from_numpy(f.astype(np.int64))
     total = total + 1e-3 * sr.LaplacianLoss(torch.from_numpy(v), fcpu).to(dev)(verts).sum() \
         + 1e-3 * sr.FlattenLoss(fcpu).to(dev)(verts).sum()

@@ -24,7 +24,8 @@ class UmrRasterParams(ctypes.Structure):
                 ("double_side", ctypes.c_int32), ("background_color", ctypes.c_float * 3),
                 ("ev_kernel_start", ctypes.c_void_p), ("ev_kernel_stop", ctypes.c_void_p),
                 ("pair_buffer", ctypes.c_void_p), ("pair_buffer_bytes", ctypes.c_uint64),
-                ("shared_textures", ctypes.c_int32), ("tile_mode", ctypes.c_int32)]
+                ("shared_textures", ctypes.c_int32), ("tile_mode", ctypes.c_int32),
+                ("color_channels", ctypes.c_int32), ("background_extra", ctypes.c_float)]
 
 
 class UmrProjectParams(ctypes.Structure):

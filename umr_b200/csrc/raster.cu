@@ -1119,14 +1119,15 @@ __device__ __forceinline__ bool bwd_pair(const float* __restrict__ rc, float xp,
 // Register-lean variant used by the pair-parallel kernel: the 10 per-pixel inputs stay in shared memory
 // (sp = &s_pix[0][pix], plane stride PT*PT) and are fetched where they are consumed, and the 9 gradients are
 // added straight into the caller's accumulators -- this keeps the kernel at <= 64 registers (4 CTAs/SM).
-template <int RGB, bool TEXGRAD>
+template <int RGB, bool TEXGRAD, int NC = 3>
 __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float xp, float yp, const Consts& K,
                                              const float* __restrict__ sp, int f, const float* __restrict__ tex_img,
                                              float* __restrict__ gtex_img, float* acc) {
     Frag fr;
     if (!fragment(rc, xp, yp, K.thr, K.sigma, fr)) return false;
-    const float g3 = sp[3 * PT * PT];
-    const float one_m_a = 1 - sp[7 * PT * PT];
+    constexpr int NP = PT * PT, NPL = NC + 1, NV = 2 * NPL + 2;  // planes: g[NC], g_alpha, C[NC], alpha, ssum, smax
+    const float g3 = sp[NC * NP];
+    const float one_m_a = 1 - sp[(2 * NC + 1) * NP];
     float Cxy = (one_m_a == 0.f || g3 == 0.f)
                     ? g3 * one_m_a
                     : (float)((double)g3 * ((double)one_m_a / fmax((double)(1 - fr.D), 1e-6)));
@@ -1137,30 +1138,30 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
     const uint32_t flg = __float_as_uint(rc[R_FLG]);
     const bool front = (flg & 8u) != 0;
     if (RGB == 0) {
-        if ((float)f == sp[9 * PT * PT]) {
+        if ((float)f == sp[(NV - 1) * NP]) {
             if (TEXGRAD) {
-                float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
-                red_add_global(gt + 0, sp[0]);
-                red_add_global(gt + 1, sp[1 * PT * PT]);
-                red_add_global(gt + 2, sp[2 * PT * PT]);
+                float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * NC;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) red_add_global(gt + c, sp[c * NP]);
             }
         }
     } else if (front || K.double_side) {
-        const float g0 = sp[0], g1 = sp[1 * PT * PT], g2 = sp[2 * PT * PT];
-        if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
+        float g[NC];
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { g[c] = sp[c * NP]; any = any || g[c] != 0.f; }
+        if (any) {
             const float zn = (K.far_ - zp) / (K.far_ - K.near_);
-            const float s = fr.D * expf((zn - sp[9 * PT * PT]) / K.gamma) / sp[8 * PT * PT];
+            const float s = fr.D * expf((zn - sp[(NV - 1) * NP]) / K.gamma) / sp[(NV - 2) * NP];
             if (s != 0.f) {
-                const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * 3;
+                const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * NC;
                 if (TEXGRAD) {
-                    red_add_global(gtex_img + to + 0, s * g0);
-                    red_add_global(gtex_img + to + 1, s * g1);
-                    red_add_global(gtex_img + to + 2, s * g2);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
                 }
                 float Crgb = 0.f;
-                Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * PT * PT]);
-                Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * PT * PT]);
-                Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * PT * PT]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) Crgb += g[c] * (__ldg(tex_img + to + c) - sp[(NPL + c) * NP]);
                 Crgb *= s;
                 if (Crgb != 0.f) {
                     Cxy += Crgb / fr.D;
@@ -1185,7 +1186,7 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
 
 // One PT x PT tile of the recompute backward (bx, by, b = tile column / row / image).  Every early exit is CTA-uniform.
 // `bar_phase` carries the mbarrier parity across the tiles a CTA processes (list-driven launch).
-template <int RGB, bool TEXGRAD>
+template <int RGB, bool TEXGRAD, int NC = 3>
 __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
                                                const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                const float* __restrict__ aggrs, const float* __restrict__ grad_images,
@@ -1199,7 +1200,8 @@ __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all
     __shared__ int s_warp_cnt[NWARP];
     __shared__ float s_ext[4];
     // PT x PT pixel tile.  PT = 32 (4x the pairs per chunk) was measured 27 % slower than 16 on C2.
-    __shared__ float s_pix[10][PT * PT];   // g0..g3, C0..C3, ssum, smax of the tile's pixels (row-major)
+    constexpr int NPL = NC + 1, NV = 2 * NPL + 2;
+    __shared__ float s_pix[NV][PT * PT];   // g[NC], g_alpha, C[NC], alpha, ssum, smax of the tile's pixels (row-major)
     __shared__ float s_xp[PT], s_yp[PT];
     __shared__ unsigned int s_cm[CHUNK], s_rm[CHUNK];  // column / row pass masks of the chunk faces
     __shared__ int s_off[CHUNK + 1];                  // prefix sums of the rectangle sizes
@@ -1229,25 +1231,27 @@ __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all
     for (int pi = tid; pi < PT * PT; pi += CTA) {
         const int px = x0 + (pi % PT), py = y0 + (pi / PT);
         const size_t np = (size_t)S * S;
-        float v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+        float v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = (k == NV - 2) ? 1.f : 0.f;
         if (px < S && py < S) {
             const size_t p = (size_t)py * S + px;
             if (K.aa) {  // avg_pool2d backward: g / 4
                 const size_t nq = (size_t)K.IS * K.IS;
                 const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * nq + q) * 0.25f;
+                for (int k = 0; k < NPL; ++k) v[k] = __ldg(grad_images + ((size_t)b * NPL + k) * nq + q) * 0.25f;
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * np + p);
+                for (int k = 0; k < NPL; ++k) v[k] = __ldg(grad_images + ((size_t)b * NPL + k) * np + p);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[4 + k] = __ldg(colors_hi + ((size_t)b * 4 + k) * np + p);
-            v[8] = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
-            v[9] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
+            for (int k = 0; k < NPL; ++k) v[NPL + k] = __ldg(colors_hi + ((size_t)b * NPL + k) * np + p);
+            v[NV - 2] = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
+            v[NV - 1] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
         }
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s_pix[k][pi] = v[k];
+        for (int k = 0; k < NV; ++k) s_pix[k][pi] = v[k];
     }
     const int ncol = min(PT, S - x0), nrow = min(PT, S - y0);  // live extent of the tile
     const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
@@ -1341,7 +1345,7 @@ __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all
                     const int col = cx0 + (local - lr * w);
                     const int row = ry0 + lr;
                     const int pix = row * PT + col;
-                    if (bwd_pair_acc<RGB, TEXGRAD>(rc, s_xp[col], s_yp[row], K, &s_pix[0][pix], f, tex_img, gtex_img, acc))
+                    if (bwd_pair_acc<RGB, TEXGRAD, NC>(rc, s_xp[col], s_yp[row], K, &s_pix[0][pix], f, tex_img, gtex_img, acc))
                         acc_any = true;
                 }
                 if (__any_sync(0xffffffffu, acc_any)) {
@@ -1351,7 +1355,7 @@ __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all
                         float v = acc[0];
 #pragma unroll
                         for (int k = 1; k < 9; ++k) v = (lane == k) ? acc[k] : v;
-                        if (v != 0.f) red_add_global(grad_faces + ((size_t)b * F + f) * 9 + lane, v);
+                        if (v != 0.f && grad_faces != nullptr) red_add_global(grad_faces + ((size_t)b * F + f) * 9 + lane, v);
                     }
                 }
             }
@@ -1365,7 +1369,7 @@ __device__ __forceinline__ void bwd_pairs_tile(const float* __restrict__ rec_all
 
 
 // full grid: one CTA per tile (no pair buffer: every tile is recomputed)
-template <int RGB, bool TEXGRAD>
+template <int RGB, bool TEXGRAD, int NC = 3>
 __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
                                                              const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                              const float* __restrict__ aggrs, const float* __restrict__ grad_images,
@@ -1377,14 +1381,14 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs(const float* __rest
         fence_mbar_init();
     }
     uint32_t phase = 0;  // (bwd_pairs_tile synchronises the CTA before the barrier is first used)
-    bwd_pairs_tile<RGB, TEXGRAD>(rec_all, box_all, textures, colors_hi, aggrs, grad_images, grad_faces, grad_tex, ubox, K,
+    bwd_pairs_tile<RGB, TEXGRAD, NC>(rec_all, box_all, textures, colors_hi, aggrs, grad_images, grad_faces, grad_tex, ubox, K,
                                  (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, &s_bar, phase);
 }
 
 // list-driven: with a pair buffer, only the tiles the forward could NOT save are recomputed.  The forward appended
 // their ids to `ulist` (count in *ucount); a small persistent grid walks the list, so a render whose tiles were all
 // saved pays one near-empty launch instead of one CTA per tile (35 us at C2 with the full grid).
-template <int RGB, bool TEXGRAD>
+template <int RGB, bool TEXGRAD, int NC = 3>
 __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs_list(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
                                                                   const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                                   const float* __restrict__ aggrs, const float* __restrict__ grad_images,
@@ -1403,7 +1407,7 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs_list(const float* _
     for (uint32_t i = blockIdx.x; i < nu; i += gridDim.x) {
         const int t = __ldg(ulist + i);
         const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-        bwd_pairs_tile<RGB, TEXGRAD>(rec_all, box_all, textures, colors_hi, aggrs, grad_images, grad_faces, grad_tex, ubox, K,
+        bwd_pairs_tile<RGB, TEXGRAD, NC>(rec_all, box_all, textures, colors_hi, aggrs, grad_images, grad_faces, grad_tex, ubox, K,
                                      bx, by, b, &s_bar, phase);
     }
 }
@@ -1472,6 +1476,7 @@ static PairBuf make_pairbuf(const UmrRasterParams* p, int S) {
     return pb;
 }
 
+static bool is_generic(const UmrRasterParams* p);
 static int check_params(const UmrRasterParams* p) {
     if (!p) return UMR_ERR_BAD_ARG;
     if (p->batch_size <= 0 || p->num_faces <= 0 || p->texture_size <= 0 || p->image_size <= 0)
@@ -1483,6 +1488,9 @@ static int check_params(const UmrRasterParams* p) {
     if (p->texture_sample_type == UMR_TEX_VERTEX && p->texture_size != 3) return UMR_ERR_BAD_ARG;  // [B,F,3,3]
     if (p->shared_textures > 1 && p->batch_size % p->shared_textures != 0) return UMR_ERR_BAD_ARG;
     if (p->func_id_rgb != UMR_RGB_HARD && p->func_id_rgb != UMR_RGB_SOFTMAX) return UMR_ERR_UNSUPPORTED;
+    if (p->color_channels != 0 && p->color_channels != 3 && p->color_channels != 4) return UMR_ERR_BAD_ARG;
+    // 4 colour channels (the part-map render): UMR's own configuration only
+    if (p->color_channels == 4 && (is_generic(p) || p->func_id_rgb != UMR_RGB_SOFTMAX)) return UMR_ERR_UNSUPPORTED;
     return UMR_OK;
 }
 
@@ -1515,7 +1523,7 @@ static Consts make_consts(const UmrRasterParams* p) {
     K.alpha = p->func_id_alpha;
     K.tex = p->texture_sample_type;
     K.vec_store = 0;
-    K.tex_bs = (size_t)p->num_faces * p->texture_size * 3;
+    K.tex_bs = (size_t)p->num_faces * p->texture_size * (p->color_channels == 4 ? 4 : 3);
     K.tex_div = p->shared_textures > 1 ? p->shared_textures : 1;
     return K;
 }
@@ -1608,12 +1616,15 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
         count_launch(2);
         k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
         if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
-        const int impl = forward_impl(F, B, K.S, p->tile_mode);
+        const bool nc4 = p->color_channels == 4;
+        const int impl = nc4 ? 3 : forward_impl(F, B, K.S, p->tile_mode);
 #define UMR_FWD_ARGS rec, box, clist, ccount, textures, images, soft_colors, aggrs_info, pacc, ubox, K, p->eps, \
                      p->background_color[0], p->background_color[1], p->background_color[2], pb, ncb
         if (impl == 2) {
             if (softmax) k_raster_fwd2<1><<<grid, CTA, fwd2_smem, stream>>>(UMR_FWD_ARGS);
             else k_raster_fwd2<0><<<grid, CTA, fwd2_smem, stream>>>(UMR_FWD_ARGS);
+        } else if (nc4) {
+            k_raster_fwd3<1, 4><<<grid, CTA, 0, stream>>>(UMR_FWD_ARGS, p->background_extra);
         } else if (impl == 3) {
             if (softmax) k_raster_fwd3<1><<<grid, CTA, 0, stream>>>(UMR_FWD_ARGS);
             else k_raster_fwd3<0><<<grid, CTA, 0, stream>>>(UMR_FWD_ARGS);
@@ -1653,10 +1664,11 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
                                    const UmrRasterParams* p, void* workspace, void* stream_) {
     int rc = check_params(p);
     if (rc) return rc;
-    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !grad_images || !grad_faces ||
-        !workspace)
-        return UMR_ERR_BAD_ARG;
+    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !grad_images || !workspace) return UMR_ERR_BAD_ARG;
+    if (!grad_faces && !grad_textures) return UMR_ERR_BAD_ARG;  // nothing to compute
     if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
+    const bool nc4 = p->color_channels == 4;
+    if (nc4 && grad_textures) return UMR_ERR_UNSUPPORTED;  // part maps are constants (loss_utils.py:367-381)
     cudaStream_t stream = (cudaStream_t)stream_;
     rc = ensure_smem_attrs();
     if (rc) return rc;
@@ -1677,12 +1689,20 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         const char* e = getenv("UMR_BWD_IMPL");
         return e && e[0] == 'r' && e[1] == 'e' && e[2] == 'c';
     }();
+    static const bool use_pairs = [] {  // UMR_BWD_IMPL=pixel selects the per-pixel formulation (A/B testing)
+        const char* e = getenv("UMR_BWD_IMPL");
+        return !(e && e[0] == 'p' && e[1] == 'i' && e[2] == 'x');
+    }();
     const PairBuf pb = (gen || no_stream) ? PairBuf{nullptr, nullptr, nullptr, nullptr, nullptr, 0u} : make_pairbuf(p, K.S);
     // (with a pair buffer the records only serve the recompute fallback: k_prep returns at once when no tile needs it)
     k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, r, pb.cap > 0 ? pb.ctrl + 1 : nullptr);
     count_launch();
-    e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
-    if (e != cudaSuccess) return (int)e;
+    if (grad_faces) {
+        e = cudaMemsetAsync(grad_faces, 0, (size_t)n * 9 * sizeof(float), stream);
+        if (e != cudaSuccess) return (int)e;
+    } else if (gen || !use_pairs) {
+        return UMR_ERR_UNSUPPORTED;  // texture-only backward: streaming / pair kernels only
+    }
     if (grad_textures) {
         e = cudaMemsetAsync(grad_textures, 0, (size_t)(n / (p->shared_textures > 1 ? p->shared_textures : 1)) * p->texture_size * 3 * sizeof(float), stream);
         if (e != cudaSuccess) return (int)e;
@@ -1690,10 +1710,6 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
     const size_t smem = raster_dyn_smem(F);
     const bool softmax = p->func_id_rgb == UMR_RGB_SOFTMAX;
-    static const bool use_pairs = [] {  // UMR_BWD_IMPL=pixel selects the per-pixel formulation (A/B testing)
-        const char* e = getenv("UMR_BWD_IMPL");
-        return !(e && e[0] == 'p' && e[1] == 'i' && e[2] == 'x');
-    }();
 #define UMR_LAUNCH_BWD(RGBM, TG)                                                                              \
     do {                                                                                                      \
         if (gen)                                                                                              \
@@ -1702,12 +1718,21 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         else if (use_pairs) {                                                                                 \
             if (pb.cap > 0) {                                                                                 \
                 count_launch();                                                                               \
-                if (forward_impl(F, B, K.S, p->tile_mode) == 4)                                                                     \
-                    k_raster_bwd2<RGBM, TG, 32><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                if (forward_impl(F, B, K.S, p->tile_mode) == 4) {                                             \
+                    if (TG && !grad_faces)                                                                    \
+                        k_raster_bwd2<RGBM, TG, 32, 3, !TG><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
                                                                             grad_faces, grad_textures, K, pb); \
-                else                                                                                          \
-                    k_raster_bwd2<RGBM, TG, 16><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                    else                                                                                      \
+                        k_raster_bwd2<RGBM, TG, 32><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
                                                                             grad_faces, grad_textures, K, pb); \
+                } else {                                                                                      \
+                    if (TG && !grad_faces)                                                                    \
+                        k_raster_bwd2<RGBM, TG, 16, 3, !TG><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                                                                            grad_faces, grad_textures, K, pb); \
+                    else                                                                                      \
+                        k_raster_bwd2<RGBM, TG, 16><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                                                                            grad_faces, grad_textures, K, pb); \
+                }                                                                                             \
             }                                                                                                 \
             if (pb.cap > 0)                                                                                   \
                 k_raster_bwd_pairs_list<RGBM, TG><<<list_grid, CTA, smem, stream>>>(                          \
@@ -1727,7 +1752,19 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     const unsigned list_grid = (unsigned)(ntiles < 444 ? ntiles : 444);  // 3 CTAs x 148 SMs walk the unsaved-tile list
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     count_launch();
-    if (softmax) {
+    if (nc4) {  // 16x16 tiles, softmax, no texture gradient (check_params / above)
+        if (pb.cap > 0) {
+            count_launch();
+            k_raster_bwd2<1, false, 16, 4><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, grad_faces,
+                                                                            grad_textures, K, pb);
+            k_raster_bwd_pairs_list<1, false, 4><<<list_grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, grad_images,
+                                                                                   grad_faces, grad_textures, ubox, K, pb.ctrl + 1,
+                                                                                   pb.ulist, (int)grid_pairs.x, (int)grid_pairs.y);
+        } else {
+            k_raster_bwd_pairs<1, false, 4><<<grid_pairs, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, grad_images,
+                                                                               grad_faces, grad_textures, ubox, K);
+        }
+    } else if (softmax) {
         if (grad_textures) UMR_LAUNCH_BWD(1, true); else UMR_LAUNCH_BWD(1, false);
     } else {
         if (grad_textures) UMR_LAUNCH_BWD(0, true); else UMR_LAUNCH_BWD(0, false);

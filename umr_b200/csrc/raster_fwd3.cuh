@@ -10,7 +10,7 @@
 
 namespace umr {
 
-template <int RGB>
+template <int RGB, int NC = 3>  // NC colour channels (3, or 4: the part-map render of SURVEY.md 8f-2); planes = NC + 1 (alpha)
 #ifndef UMR_FWD3_CTAS
 #define UMR_FWD3_CTAS 4
 #endif
@@ -20,7 +20,9 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                                                         float* __restrict__ colors_hi, float* __restrict__ aggrs,
                                                         float* __restrict__ p2f_acc, const uint32_t* __restrict__ ubox,
                                                         Consts K, float eps, float bg0, float bg1, float bg2, PairBuf pb,
-                                                        int ncb) {
+                                                        int ncb, float bg3 = 0.f) {
+    constexpr int NPL = NC + 1;                                      // image planes: colours + alpha
+    const float bgc[4] = {bg0, bg1, bg2, bg3};
     constexpr int WG = 16;                                           // list entries per warp group
     __shared__ __align__(128) float s_wrec[NWARP * 2 * WG * REC_F];  // 32 KB: warp-private record stages; reused by the store epilogue
     float* s_rec = s_wrec;
@@ -54,45 +56,47 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
         // general path (kernel.cu:335-348, 443-475), evaluated once, stored with 128-bit stores where possible.
         if (tid == 0 && pb.cap > 0) pb.tile_head[tile_id] = TILE_EMPTY;
         const float ssum0 = expf(eps / K.gamma);
-        float o0, o1, o2, g0, g1;
+        float full[NC + 3], g0, g1;
         if (RGB == 0) {
-            o0 = bg0; o1 = bg1; o2 = bg2;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) full[k] = bgc[k];
             g0 = 10000000.f; g1 = -1.f;
         } else {
-            const float q0 = bg0 * ssum0, q1 = bg1 * ssum0, q2 = bg2 * ssum0;
-            o0 = q0 == 0.f ? q0 : q0 / ssum0;
-            o1 = q1 == 0.f ? q1 : q1 / ssum0;
-            o2 = q2 == 0.f ? q2 : q2 / ssum0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const float q = bgc[k] * ssum0;
+                full[k] = q == 0.f ? q : q / ssum0;
+            }
             g0 = ssum0; g1 = eps;
         }
-        const float alpha = (float)(1. - (double)1.f);
-        const float full[6] = {o0, o1, o2, alpha, g0, g1};
-        float pooled[4];
+        full[NC] = (float)(1. - (double)1.f);  // alpha
+        full[NC + 1] = g0; full[NC + 2] = g1;
+        float pooled[NPL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pooled[k] = (((full[k] + full[k]) + full[k]) + full[k]) * 0.25f;
+        for (int k = 0; k < NPL; ++k) pooled[k] = (((full[k] + full[k]) + full[k]) + full[k]) * 0.25f;
         if (K.aa && K.vec_store && tx0 + TILE <= S && ty0 + TILE <= S) {
-            for (int i = tid; i < 6 * 64; i += CTA) {
+            for (int i = tid; i < (NC + 3) * 64; i += CTA) {
                 const int plane = i >> 6, rem = i & 63, row = rem >> 2, q = rem & 3;
                 float x = full[0];
 #pragma unroll
-                for (int k = 1; k < 6; ++k) x = (plane == k) ? full[k] : x;
+                for (int k = 1; k < NC + 3; ++k) x = (plane == k) ? full[k] : x;
                 const float4 val = make_float4(x, x, x, x);
                 const size_t off = (size_t)(ty0 + row) * S + tx0 + q * 4;
-                if (plane < 4) {
+                if (plane < NPL) {
                     if (colors_hi != nullptr)
-                        *reinterpret_cast<float4*>(colors_hi + ((size_t)b * 4 + plane) * np + off) = val;
+                        *reinterpret_cast<float4*>(colors_hi + ((size_t)b * NPL + plane) * np + off) = val;
                 } else {
-                    *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - 4)) * np + off) = val;
+                    *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - NPL)) * np + off) = val;
                 }
             }
-            if (tid < 64) {
+            if (tid < NPL * 16) {
                 const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
                 float x = pooled[0];
 #pragma unroll
-                for (int kk = 1; kk < 4; ++kk) x = (k == kk) ? pooled[kk] : x;
+                for (int kk = 1; kk < NPL; ++kk) x = (k == kk) ? pooled[kk] : x;
                 const int IS = K.IS;
                 const size_t nq = (size_t)IS * IS;
-                *reinterpret_cast<float4*>(images + ((size_t)b * 4 + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) =
+                *reinterpret_cast<float4*>(images + ((size_t)b * NPL + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) =
                     make_float4(x, x, x, x);
             }
             return;
@@ -104,18 +108,18 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
             aggrs[((size_t)b * 2 + 1) * np + p] = g1;
             if (colors_hi != nullptr) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) colors_hi[((size_t)b * 4 + k) * np + p] = full[k];
+                for (int k = 0; k < NPL; ++k) colors_hi[((size_t)b * NPL + k) * np + p] = full[k];
             }
             if (K.aa) {
                 if ((px & 1) == 0 && (py & 1) == 0 && px + 1 < S && py + 1 < S) {
                     const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
                     const size_t nq = (size_t)K.IS * K.IS;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * nq + q] = pooled[k];
+                    for (int k = 0; k < NPL; ++k) images[((size_t)b * NPL + k) * nq + q] = pooled[k];
                 }
             } else if (images != colors_hi) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * np + p] = full[k];
+                for (int k = 0; k < NPL; ++k) images[((size_t)b * NPL + k) * np + p] = full[k];
             }
         }
         return;
@@ -137,9 +141,9 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
     float acc_a = 1.f;
     float ssum = expf(eps / K.gamma);
     float smax = eps;
-    float c0, c1, c2;
-    if (RGB == 1) { c0 = bg0 * ssum; c1 = bg1 * ssum; c2 = bg2 * ssum; }
-    else { c0 = bg0; c1 = bg1; c2 = bg2; }
+    float col[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) col[k] = RGB == 1 ? bgc[k] * ssum : bgc[k];
     float zmin = 10000000.f;
     int fid = -1;
     // torch-1.1 affine_grid (align_corners=True) coordinates of this pixel: linspace(-1, 1, S)
@@ -320,8 +324,9 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                                 if (zp < zmin && inside && (K.double_side || front)) {
                                     zmin = zp;
                                     fid = f;
-                                    const float* tp = tex_img + ((size_t)f * K.T2 + tix) * 3;
-                                    c0 = __ldg(tp); c1 = __ldg(tp + 1); c2 = __ldg(tp + 2);
+                                    const float* tp = tex_img + ((size_t)f * K.T2 + tix) * NC;
+#pragma unroll
+                                    for (int k = 0; k < NC; ++k) col[k] = __ldg(tp + k);
                                 }
                             } else {
                                 // normalised depth (kernel.cu:418); the backward needs THESE bits (its softmax weight is
@@ -338,10 +343,9 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                                     if (a != 0.f || ed != 1.f) {
                                         a_x = a * gx; a_y = a * gy; a_w = a;
                                         contrib = a != 0.f;
-                                        const float* tp = tex_img + ((size_t)f * K.T2 + tix) * 3;
-                                        c0 = ed * c0 + a * __ldg(tp);
-                                        c1 = ed * c1 + a * __ldg(tp + 1);
-                                        c2 = ed * c2 + a * __ldg(tp + 2);
+                                        const float* tp = tex_img + ((size_t)f * K.T2 + tix) * NC;
+#pragma unroll
+                                        for (int k = 0; k < NC; ++k) col[k] = ed * col[k] + a * __ldg(tp + k);
                                     }
                                 }
                             }
@@ -390,20 +394,22 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
 
     // ---- finalise (kernel.cu:443-475) + fused 2x2 pool + coalesced stores (as round 1) --------------------
     const float alpha = (float)(1. - (double)acc_a);  // kernel.cu:449-451
-    float o0, o1, o2, g0, g1;
+    float v[NPL], hi[NPL], g0, g1;  // hi: full-resolution planes, v: pooled
     if (RGB == 0) {
-        o0 = c0; o1 = c1; o2 = c2;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) hi[k] = col[k];
         g0 = zmin; g1 = (float)fid;
     } else {
-        o0 = c0 == 0.f ? c0 : c0 / ssum;
-        o1 = c1 == 0.f ? c1 : c1 / ssum;
-        o2 = c2 == 0.f ? c2 : c2 / ssum;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) hi[k] = col[k] == 0.f ? col[k] : col[k] / ssum;
         g0 = ssum; g1 = smax;
     }
-    float v[4] = {o0, o1, o2, alpha};
+    hi[NC] = alpha;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) v[k] = hi[k];
     if (K.aa) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NPL; ++k) {
             const float a01 = __shfl_xor_sync(0xffffffffu, v[k], 1);
             const float a10 = __shfl_xor_sync(0xffffffffu, v[k], 8);
             const float a11 = __shfl_xor_sync(0xffffffffu, v[k], 9);
@@ -411,33 +417,34 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
         }
     }
     if (K.aa && K.vec_store && tx0 + TILE <= S && ty0 + TILE <= S) {  // uniform: full tile, aligned buffers
-        float* st = s_rec;  // 6 * 256 + 4 * 64 = 1792 floats <= 2048
+        float* st = s_rec;  // (NC + 3) * 256 + (NC + 1) * 64 floats (2112 for NC = 4) <= 8192
         const int o = lrow * TILE + lcol;
-        st[0 * 256 + o] = o0; st[1 * 256 + o] = o1; st[2 * 256 + o] = o2; st[3 * 256 + o] = alpha;
-        st[4 * 256 + o] = g0; st[5 * 256 + o] = g1;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) st[k * 256 + o] = hi[k];
+        st[NPL * 256 + o] = g0; st[(NPL + 1) * 256 + o] = g1;
         if ((lane & 1) == 0 && (lane & 8) == 0) {
             const int po = (lrow >> 1) * (TILE / 2) + (lcol >> 1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) st[6 * 256 + k * 64 + po] = v[k];
+            for (int k = 0; k < NPL; ++k) st[(NC + 3) * 256 + k * 64 + po] = v[k];
         }
         __syncthreads();
-        for (int i = tid; i < 6 * 64; i += CTA) {
+        for (int i = tid; i < (NC + 3) * 64; i += CTA) {
             const int plane = i >> 6, rem = i & 63, row = rem >> 2, q = rem & 3;
             const float4 val = *reinterpret_cast<const float4*>(st + plane * 256 + row * TILE + q * 4);
             const size_t off = (size_t)(ty0 + row) * S + tx0 + q * 4;
-            if (plane < 4) {
+            if (plane < NPL) {
                 if (colors_hi != nullptr)
-                    *reinterpret_cast<float4*>(colors_hi + ((size_t)b * 4 + plane) * np + off) = val;
+                    *reinterpret_cast<float4*>(colors_hi + ((size_t)b * NPL + plane) * np + off) = val;
             } else {
-                *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - 4)) * np + off) = val;
+                *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - NPL)) * np + off) = val;
             }
         }
-        if (tid < 64) {
+        if (tid < NPL * 16) {
             const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
-            const float4 val = *reinterpret_cast<const float4*>(st + 6 * 256 + k * 64 + row * (TILE / 2) + q * 4);
+            const float4 val = *reinterpret_cast<const float4*>(st + (NC + 3) * 256 + k * 64 + row * (TILE / 2) + q * 4);
             const int IS = K.IS;
             const size_t nq = (size_t)IS * IS;
-            *reinterpret_cast<float4*>(images + ((size_t)b * 4 + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) = val;
+            *reinterpret_cast<float4*>(images + ((size_t)b * NPL + k) * nq + (size_t)((ty0 >> 1) + row) * IS + (tx0 >> 1) + q * 4) = val;
         }
         return;
     }
@@ -446,10 +453,8 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
         aggrs[((size_t)b * 2 + 0) * np + p] = g0;
         aggrs[((size_t)b * 2 + 1) * np + p] = g1;
         if (colors_hi != nullptr) {
-            colors_hi[((size_t)b * 4 + 0) * np + p] = o0;
-            colors_hi[((size_t)b * 4 + 1) * np + p] = o1;
-            colors_hi[((size_t)b * 4 + 2) * np + p] = o2;
-            colors_hi[((size_t)b * 4 + 3) * np + p] = alpha;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) colors_hi[((size_t)b * NPL + k) * np + p] = hi[k];
         }
     }
     if (K.aa) {
@@ -458,14 +463,12 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
             const size_t q = (size_t)(py >> 1) * IS + (px >> 1);
             const size_t nq = (size_t)IS * IS;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) images[((size_t)b * 4 + k) * nq + q] = v[k];
+            for (int k = 0; k < NPL; ++k) images[((size_t)b * NPL + k) * nq + q] = v[k];
         }
     } else if (live && images != colors_hi) {
         const size_t p = (size_t)py * S + px;
-        images[((size_t)b * 4 + 0) * np + p] = o0;
-        images[((size_t)b * 4 + 1) * np + p] = o1;
-        images[((size_t)b * 4 + 2) * np + p] = o2;
-        images[((size_t)b * 4 + 3) * np + p] = alpha;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) images[((size_t)b * NPL + k) * np + p] = hi[k];
     }
 }
 

@@ -650,12 +650,15 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
 #define UMR_BWD2_CTAS 4
 #endif
 // TS: side of the forward's tile (16: k_raster_fwd3 / k_raster_fwd2, 32: k_raster_fwd4); one CTA streams one tile
-template <int RGB, bool TEXGRAD, int TS>
+// GEOM = false: the caller wants no gradient for the vertices (UMR's texture branch renders DETACHED geometry,
+// experiments/train_s2.py:248) -- only the texel gradients are formed, the compiler drops the rest of the arithmetic.
+template <int RGB, bool TEXGRAD, int TS, int NC = 3, bool GEOM = true>  // NC colour channels; pixel planes: g[NC], g_alpha, C[NC], alpha, ssum, smax
 __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                         const float* __restrict__ aggrs, const float* __restrict__ grad_images,
                                                         float* __restrict__ grad_faces, float* __restrict__ grad_tex, Consts K,
                                                         PairBuf pb) {
-    __shared__ float s_pix[10][TS * TS];  // g0..g3, C0..C3, ssum, smax (row-major tile pixels)
+    constexpr int NPL = NC + 1, NV = 2 * NPL + 2;
+    __shared__ float s_pix[NV][TS * TS];  // g[NC], g_alpha, C[NC], alpha, ssum, smax (row-major tile pixels)
     constexpr int NP = TS * TS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
@@ -667,25 +670,27 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
     for (int pi = tid; pi < NP; pi += CTA) {
         const int px = x0 + (pi % TS), py = y0 + (pi / TS);
         const size_t np = (size_t)S * S;
-        float v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+        float v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = (k == NV - 2) ? 1.f : 0.f;
         if (px < S && py < S) {
             const size_t p = (size_t)py * S + px;
             if (K.aa) {  // avg_pool2d backward: g / 4
                 const size_t nq = (size_t)K.IS * K.IS;
                 const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * nq + q) * 0.25f;
+                for (int k = 0; k < NPL; ++k) v[k] = __ldg(grad_images + ((size_t)b * NPL + k) * nq + q) * 0.25f;
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = __ldg(grad_images + ((size_t)b * 4 + k) * np + p);
+                for (int k = 0; k < NPL; ++k) v[k] = __ldg(grad_images + ((size_t)b * NPL + k) * np + p);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[4 + k] = __ldg(colors_hi + ((size_t)b * 4 + k) * np + p);
-            v[8] = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
-            v[9] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
+            for (int k = 0; k < NPL; ++k) v[NPL + k] = __ldg(colors_hi + ((size_t)b * NPL + k) * np + p);
+            v[NV - 2] = __ldg(aggrs + ((size_t)b * 2 + 0) * np + p);
+            v[NV - 1] = __ldg(aggrs + ((size_t)b * 2 + 1) * np + p);
         }
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s_pix[k][pi] = v[k];
+        for (int k = 0; k < NV; ++k) s_pix[k][pi] = v[k];
     }
     __syncthreads();
     const float* tex_img = textures + (size_t)(b / K.tex_div) * K.tex_bs;
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
     int cur_f = -1;
     auto flush = [&]() {
-        if (cur_f >= 0) {
+        if (GEOM && cur_f >= 0) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
             if (lane < 9) {
@@ -810,37 +815,42 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
                 const int tix = TS == 16 ? (int)((meta >> 8) & 0xffffu) : (int)((meta >> 10) & 0x3fffu);
                 const bool front = (meta >> 24) & 1u;
                 const float* sp = &s_pix[0][pix];
-                const float g3 = sp[3 * NP];
-                const float one_m_a = 1 - sp[7 * NP];
-                // g3 * ((1 - alpha) / max(1 - D, 1e-6)) (kernel.cu:584), in fp32 (the reference promotes to double;
-                // gradients are compared at 1e-4, see DESIGN.md "backward arithmetic")
-                float Cxy = (one_m_a == 0.f || g3 == 0.f) ? g3 * one_m_a : g3 * __fdividef(one_m_a, fmaxf(1 - D, 1e-6f));
+                float Cxy = 0.f;
+                if (GEOM) {
+                    const float g3 = sp[NC * NP];  // gradient of alpha
+                    const float one_m_a = 1 - sp[(2 * NC + 1) * NP];
+                    // g3 * ((1 - alpha) / max(1 - D, 1e-6)) (kernel.cu:584), in fp32 (the reference promotes to double;
+                    // gradients are compared at 1e-4, see DESIGN.md "backward arithmetic")
+                    Cxy = (one_m_a == 0.f || g3 == 0.f) ? g3 * one_m_a : g3 * __fdividef(one_m_a, fmaxf(1 - D, 1e-6f));
+                }
                 if (RGB == 0) {
-                    if ((float)f == sp[9 * NP]) {  // aggrs[1] = winning face id (:596)
+                    if ((float)f == sp[(NV - 1) * NP]) {  // aggrs[1] = winning face id (:596)
                         if (TEXGRAD) {
-                            float* gt = gtex_img + ((size_t)f * K.T2 + tix) * 3;
-                            red_add_global(gt + 0, sp[0]);
-                            red_add_global(gt + 1, sp[1 * NP]);
-                            red_add_global(gt + 2, sp[2 * NP]);
+                            float* gt = gtex_img + ((size_t)f * K.T2 + tix) * NC;
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) red_add_global(gt + c, sp[c * NP]);
                         }
                     }
                 } else if (front || K.double_side) {
-                    const float g0 = sp[0], g1 = sp[1 * NP], g2 = sp[2 * NP];
-                    if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
-                        const float s = __fdividef(D * expf((zn - sp[9 * NP]) * K.r_gamma), sp[8 * NP]);  // :608
+                    float g[NC];
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) { g[c] = sp[c * NP]; any = any || g[c] != 0.f; }
+                    if (any) {
+                        const float s = __fdividef(D * expf((zn - sp[(NV - 1) * NP]) * K.r_gamma), sp[(NV - 2) * NP]);  // :608
                         if (s != 0.f) {
-                            const size_t to = ((size_t)f * K.T2 + tix) * 3;
+                            const size_t to = ((size_t)f * K.T2 + tix) * NC;
                             if (TEXGRAD) {
-                                red_add_global(gtex_img + to + 0, s * g0);
-                                red_add_global(gtex_img + to + 1, s * g1);
-                                red_add_global(gtex_img + to + 2, s * g2);
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
                             }
                             float Crgb = 0.f;
-                            Crgb += g0 * (__ldg(tex_img + to + 0) - sp[4 * NP]);
-                            Crgb += g1 * (__ldg(tex_img + to + 1) - sp[5 * NP]);
-                            Crgb += g2 * (__ldg(tex_img + to + 2) - sp[6 * NP]);
-                            Crgb *= s;
-                            if (Crgb != 0.f) {
+                            if (GEOM) {
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) Crgb += g[c] * (__ldg(tex_img + to + c) - sp[(NPL + c) * NP]);
+                                Crgb *= s;
+                            }
+                            if (GEOM && Crgb != 0.f) {
                                 Cxy += __fdividef(Crgb, D);
                                 const float zp = K.far_ - zn * (K.far_ - K.near_);
                                 const float Cz = Crgb * K.r_gamma * K.r_nf * zp * zp;  // :624
@@ -851,14 +861,16 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
                         }
                     }
                 }
-                Cxy *= D * (1 - D) * K.r_sigma;  // :632
-                const float q = 2 * Cxy;          // :640 (the sign rides in sdx / sdy)
-                acc[0] += q * r1.x * sdx;
-                acc[1] += q * r1.x * sdy;
-                acc[3] += q * r1.y * sdx;
-                acc[4] += q * r1.y * sdy;
-                acc[6] += q * r1.z * sdx;
-                acc[7] += q * r1.z * sdy;
+                if (GEOM) {
+                    Cxy *= D * (1 - D) * K.r_sigma;  // :632
+                    const float q = 2 * Cxy;          // :640 (the sign rides in sdx / sdy)
+                    acc[0] += q * r1.x * sdx;
+                    acc[1] += q * r1.x * sdy;
+                    acc[3] += q * r1.y * sdx;
+                    acc[4] += q * r1.y * sdy;
+                    acc[6] += q * r1.z * sdx;
+                    acc[7] += q * r1.z * sdy;
+                }
             }
             f_c = f_n; act_c = act_n; src_c = src_n; have = have_n;
             c0r = n0r; c1r = n1r; c2r = n2r;

@@ -326,6 +326,8 @@ class part_matching_loss(nn.Module):
         n = batch_size * num_cam
         for k in (1, 2, 3, 4):
             self.register_buffer("stex%d" % k, stex_one_hot[:, :, :, k].unsqueeze(-1).repeat(n, 1, 1, 3))
+        # the four part maps as ONE batch-shared 4-channel texture for the single-render path
+        self.register_buffer("stex_parts", stex_one_hot[:, :, :, 1:5].contiguous().float(), persistent=False)
         self.renderer = SoftRenderer(im_size, "softmax")
         self.renderer.ambient_light_only()
         self.kl = nn.KLDivLoss(reduction="batchmean")
@@ -334,15 +336,20 @@ class part_matching_loss(nn.Module):
         self.register_buffer("proj", proj)
         self.register_buffer("weights", torch.tensor([0, 5.0, 0.0, 0.0, 5.0]).view(1, 5, 1, 1))
         self.loss_type = loss_type
-        self.pack_parts = True  # 2 packed renders instead of the reference's 4 (same values)
+        self.pack_parts = True  # ONE 4-channel render (CUDA) / 2 packed renders instead of the reference's 4 (same values)
 
     def forward(self, verts, faces, cams, part_segs, cam_probs=None, avg=True):
         bs = verts.size(0)
-        if self.pack_parts:
+        if self.pack_parts and verts.is_cuda and self.renderer._fusable(verts):
             # The reference renders each one-hot part map as its own 3-identical-channel image (4 renders,
-            # loss_utils.py:385-399).  Colour channels never interact in the rasteriser, so parts 1-3 ride
-            # in the R/G/B channels of ONE render and part 4 in a second: 2 renders, identical values.  The
-            # channel-mean of the reference (mean of three equal numbers) is reproduced on a stacked copy.
+            # loss_utils.py:385-399).  Colour channels never interact in the rasteriser, so the four maps ride in the
+            # four colour channels of ONE render (`color_channels = 4` kernels, one batch-shared [1,F,T2,4] texture):
+            # one raster launch, identical values.  The channel-mean of the reference (mean of three equal numbers) is
+            # reproduced on an expanded view.
+            p, _, _ = self.renderer(verts, faces, cams, self.stex_parts)
+            projs = [torch.mean(p[:, k:k + 1].expand(-1, 3, -1, -1), dim=1).unsqueeze(1) for k in range(4)]
+        elif self.pack_parts:
+            # generic path: parts 1-3 in the R/G/B channels of one render and part 4 in a second
             tex123 = torch.stack((self.stex1[:bs, :, :, 0], self.stex2[:bs, :, :, 0], self.stex3[:bs, :, :, 0]), dim=-1)
             p123, _, _ = self.renderer(verts, faces, cams, tex123)
             p4, _, _ = self.renderer(verts, faces, cams, self.stex4[:bs])

@@ -190,18 +190,28 @@ class SoftRasterizeFunction(torch.autograd.Function):
         group = B // Bt
         tex = textures.detach().contiguous().float()
         T2 = tex.shape[2]
+        # colour channels: 3, or 4 for the one-render part maps of part_matching_loss; images then
+        # carry NC + 1 planes (colours + alpha)
+        NC = int(tex.shape[-1]) if texture_type == "surface" else 3
+        if NC not in (3, 4):
+            raise ValueError("textures must have 3 (or, surface textures only, 4) colour channels, got %d" % NC)
         S = int(image_size) * (2 if anti_aliasing else 1)
         params = make_params(B, F, T2, image_size, anti_aliasing, background_color, near, far, fill_back,
                              eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb,
                              aggr_func_alpha, texture_type)
         params.shared_textures = group if group > 1 else 0
         params.tile_mode = FORWARD_TILE
+        params.color_channels = NC
+        if NC == 4:
+            params.background_extra = float(background_color[3]) if len(background_color) > 3 else 0.0
+            if textures.requires_grad:
+                raise ValueError("4-channel (part-map) textures are constants: no texture gradient is built")
         need_bwd = face_vertices.requires_grad or textures.requires_grad
         _attach_events(params, "fwd")
         with torch.cuda.device(dev):
-            images = torch.empty(B, 4, image_size, image_size, device=dev, dtype=torch.float32)
+            images = torch.empty(B, NC + 1, image_size, image_size, device=dev, dtype=torch.float32)
             if anti_aliasing:
-                colors_hi = torch.empty(B, 4, S, S, device=dev, dtype=torch.float32) if need_bwd else None
+                colors_hi = torch.empty(B, NC + 1, S, S, device=dev, dtype=torch.float32) if need_bwd else None
             else:
                 colors_hi = images
             aggrs = torch.empty(B, 2, S, S, device=dev, dtype=torch.float32)
@@ -230,6 +240,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
         ctx.params = params
         ctx.in_shape = tuple(face_vertices.shape)
         ctx.tex_needs_grad = textures.requires_grad
+        ctx.geom_needs_grad = face_vertices.requires_grad
         ctx.has_pairs = pairs is not None
         if need_bwd:
             if pairs is not None:
@@ -252,7 +263,9 @@ class SoftRasterizeFunction(torch.autograd.Function):
         g = grad_images.contiguous().float()
         _attach_events(ctx.params, "bwd")
         with torch.cuda.device(dev):
-            grad_faces = torch.empty_like(fv)
+            # detached geometry (UMR's texture branch, train_s2.py:248): texture-only backward, no vertex arithmetic
+            tex_only = ctx.tex_needs_grad and not ctx.geom_needs_grad and ctx.has_pairs
+            grad_faces = None if tex_only else torch.empty_like(fv)
             grad_tex = torch.empty_like(tex) if ctx.tex_needs_grad else None
             ws = torch.empty(lib.umr_raster_workspace_bytes(B, F, ctx.params.image_size, ctx.params.anti_aliasing),
                              device=dev, dtype=torch.uint8)
@@ -261,7 +274,7 @@ class SoftRasterizeFunction(torch.autograd.Function):
                                          _ptr(ws), _stream_ptr(dev))
         _lib.check(rc, "umr_raster_backward")
         ctx.params.ev_kernel_start = ctx.params.ev_kernel_stop = None
-        return (grad_faces.view(ctx.in_shape), grad_tex) + (None,) * 14
+        return (None if grad_faces is None else grad_faces.view(ctx.in_shape), grad_tex) + (None,) * 14
 
 
 def soft_rasterize(face_vertices, textures, image_size=256, background_color=(0, 0, 0), near=1, far=100,
