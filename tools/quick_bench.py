@@ -48,6 +48,43 @@ def main():
             sv[4].numel() / 1e6, st[0], st[0] * 32.0 / (a.B * S * S), st[1]))
     print("B=%d is=%d F=%d T2=%d %s: fwd %.3f ms  bwd %.3f ms  -> %.0f img/s (fwd+bwd), alpha mean %.4f" % (
         a.B, a.isz, f.shape[0], a.R * a.R, a.rgb, tf, tb, a.B / ((tf + tb) * 1e-3), img[:, 3].mean().item()))
+    if a.rgb != "softmax":
+        return
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        sink = []
+        raster.set_profile_sink(sink)
+        for _ in range(a.iters):
+            fn()
+        torch.cuda.synchronize()
+        raster.set_profile_sink(None)
+        pr = raster.collect_profile(sink)
+        return sum(pr["fwd"]) / a.iters, sum(pr["bwd"]) / a.iters
+
+    # (1) texture-only backward: detached geometry (UMR's texture branch), kernel time from the library's own events
+    fvd = fv.detach()
+    kf_full = timed(lambda: raster.soft_rasterize(fv, tex, a.isz, **kw)[0].backward(g))
+    kf_tex = timed(lambda: raster.soft_rasterize(fvd, tex, a.isz, **kw)[0].backward(g))
+    print("kernel time  full backward: fwd %.3f bwd %.3f ms | texture-only backward (detached geometry): fwd %.3f bwd %.3f ms"
+          % (kf_full + kf_tex))
+    # (2) the four part maps of part_matching_loss: one 4-channel render vs the 2 packed / 4 separate 3-channel renders
+    F = f.shape[0]
+    parts = torch.zeros(1, F, a.R * a.R, 5, device="cuda")
+    parts.scatter_(3, torch.randint(0, 5, (1, F, a.R * a.R, 1), device="cuda"), 1.0)
+    t4 = parts[..., 1:5].contiguous()
+    t3 = [parts[..., k:k + 1].repeat(1, 1, 1, 3) for k in (1, 2, 3, 4)]
+    g5, g4 = torch.randn(a.B, 5, a.isz, a.isz, device="cuda"), torch.randn(a.B, 4, a.isz, a.isz, device="cuda")
+    one = timed(lambda: raster.soft_rasterize(fv, t4, a.isz, **kw)[0].backward(g5))
+
+    def four():
+        for t in t3:
+            raster.soft_rasterize(fv, t, a.isz, **kw)[0].backward(g4)
+    sep = timed(four)
+    print("part maps: ONE 4-channel render fwd %.3f + bwd %.3f ms  vs  4 x 3-channel renders (reference pattern) fwd %.3f + bwd %.3f ms"
+          % (one + sep))
 
 
 if __name__ == "__main__":

@@ -358,7 +358,6 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
             }
         }
 
-        const int nchunk = (n + CHUNK - 1) / CHUNK;
         issue_chunk(rec_img, s_list, n, 0, s_rec);
         issue_chunk(rec_img, s_list, n, 1, s_rec);
         cp_async_wait<1>();
@@ -778,8 +777,8 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
             }
             return false;
         };
-        // The records of step i + 1 are LOADED INTO REGISTERS while step i is processed (12 registers; UMR_BWD2_REGPIPE=0
-        // falls back to an L1 prefetch hint): the loads' latency is then covered by a whole step of arithmetic.
+        // The records of step i + 1 are prefetched into L1 while step i is processed, so the loads' latency is covered by a
+        // whole step of arithmetic.  -DUMR_BWD2_REGPIPE=1 loads them into 12 registers instead: measured equal.
         auto load3 = [&](bool act, const float4* p, float4& a, float4& b_, float4& c) {
 #if UMR_BWD2_REGPIPE
             if (act) { a = __ldg(p); b_ = __ldg(p + 32); c = __ldg(p + 64); }
