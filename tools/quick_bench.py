@@ -68,8 +68,10 @@ def main():
     fvd = fv.detach()
     kf_full = timed(lambda: raster.soft_rasterize(fv, tex, a.isz, **kw)[0].backward(g))
     kf_tex = timed(lambda: raster.soft_rasterize(fvd, tex, a.isz, **kw)[0].backward(g))
+    texd = tex.detach()
+    kf_geo = timed(lambda: raster.soft_rasterize(fv, texd, a.isz, **kw)[0].backward(g))
     print("kernel time  full backward: fwd %.3f bwd %.3f ms | texture-only backward (detached geometry): fwd %.3f bwd %.3f ms"
-          % (kf_full + kf_tex))
+          " | geometry-only backward (constant textures): fwd %.3f bwd %.3f ms" % (kf_full + kf_tex + kf_geo))
     # (2) the four part maps of part_matching_loss: one 4-channel render vs the 2 packed / 4 separate 3-channel renders
     F = f.shape[0]
     parts = torch.zeros(1, F, a.R * a.R, 5, device="cuda")

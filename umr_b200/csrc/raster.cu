@@ -1423,6 +1423,26 @@ __global__ void __launch_bounds__(CTA, 3) k_raster_bwd_pairs_list(const float* _
 // =============================================================================================
 using namespace umr;
 
+// k_raster_bwd2 instantiation for the call: texture-only (grad_faces == NULL) and warp-level texel pre-reduction variants
+// exist for the texture-gradient kernels only
+template <int RGBM, bool TG, int TS>
+static void launch_bwd2(dim3 grid, cudaStream_t stream, bool pre, const float* textures, const float* soft_colors,
+                        const float* aggrs_info, const float* grad_images, float* grad_faces, float* grad_textures,
+                        const Consts& K, const PairBuf& pb) {
+#define UMR_BWD2_GO(GEOMV, PREV) \
+    k_raster_bwd2<RGBM, TG, TS, 3, GEOMV, PREV><<<grid, BWD2_THREADS, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
+                                                                                    grad_faces, grad_textures, K, pb)
+    if constexpr (TG && RGBM == 1) {
+        if (pre) { if (grad_faces) UMR_BWD2_GO(true, true); else UMR_BWD2_GO(false, true); }
+        else { if (grad_faces) UMR_BWD2_GO(true, false); else UMR_BWD2_GO(false, false); }
+    } else if constexpr (TG) {
+        if (grad_faces) UMR_BWD2_GO(true, false); else UMR_BWD2_GO(false, false);
+    } else {
+        UMR_BWD2_GO(true, false);
+    }
+#undef UMR_BWD2_GO
+}
+
 // Which forward serves the UMR configuration: 4 = k_raster_fwd4 (32x32 tiles, dynamic 8x4 pixel blocks; tile list in
 // shared memory sized by F), 3 = k_raster_fwd3 (16x16 tiles, windowed list: any F), 2 = k_raster_fwd2 (pair-parallel,
 // kept for A/B).  Forward and backward must agree (the pair records' pixel index is relative to the forward's tile).
@@ -1476,6 +1496,15 @@ static PairBuf make_pairbuf(const UmrRasterParams* p, int S) {
     return pb;
 }
 
+// raster pixels per texel of the mesh, S^2 / (F * T2), from which the warp-level texel pre-reduction of k_raster_bwd2 is on
+// (same-box A/B, profiles/r02_texgrad_pre_ab.txt: at 91 it saves 9 % of the full and 25 % of the texture-only backward, at 23
+// it costs the full backward 7-17 % and saves the texture-only one 4-13 %, at 6 (C2) it costs both)
+#ifndef UMR_TEXGRAD_PRE_RATIO_FULL
+#define UMR_TEXGRAD_PRE_RATIO_FULL 48.0
+#endif
+#ifndef UMR_TEXGRAD_PRE_RATIO_TEXONLY
+#define UMR_TEXGRAD_PRE_RATIO_TEXONLY 20.0
+#endif
 static bool is_generic(const UmrRasterParams* p);
 static int check_params(const UmrRasterParams* p) {
     if (!p) return UMR_ERR_BAD_ARG;
@@ -1718,21 +1747,12 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
         else if (use_pairs) {                                                                                 \
             if (pb.cap > 0) {                                                                                 \
                 count_launch();                                                                               \
-                if (forward_impl(F, B, K.S, p->tile_mode) == 4) {                                             \
-                    if (TG && !grad_faces)                                                                    \
-                        k_raster_bwd2<RGBM, TG, 32, 3, !TG><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
-                                                                            grad_faces, grad_textures, K, pb); \
-                    else                                                                                      \
-                        k_raster_bwd2<RGBM, TG, 32><<<grid32, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
-                                                                            grad_faces, grad_textures, K, pb); \
-                } else {                                                                                      \
-                    if (TG && !grad_faces)                                                                    \
-                        k_raster_bwd2<RGBM, TG, 16, 3, !TG><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
-                                                                            grad_faces, grad_textures, K, pb); \
-                    else                                                                                      \
-                        k_raster_bwd2<RGBM, TG, 16><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, \
-                                                                            grad_faces, grad_textures, K, pb); \
-                }                                                                                             \
+                if (forward_impl(F, B, K.S, p->tile_mode) == 4)                                               \
+                    launch_bwd2<RGBM, TG, 32>(grid32, stream, tex_pre, textures, soft_colors, aggrs_info, grad_images, \
+                                              grad_faces, grad_textures, K, pb);                              \
+                else                                                                                          \
+                    launch_bwd2<RGBM, TG, 16>(grid_pairs, stream, tex_pre, textures, soft_colors, aggrs_info, grad_images, \
+                                              grad_faces, grad_textures, K, pb);                              \
             }                                                                                                 \
             if (pb.cap > 0)                                                                                   \
                 k_raster_bwd_pairs_list<RGBM, TG><<<list_grid, CTA, smem, stream>>>(                          \
@@ -1748,6 +1768,15 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     } while (0)
     const dim3 grid_pairs((K.S + PT - 1) / PT, (K.S + PT - 1) / PT, B);
     const dim3 grid32((K.S + T4 - 1) / T4, (K.S + T4 - 1) / T4, B);
+    // texel-gradient pre-reduction inside the warp (k_raster_bwd2<..., PRE>): pays when many pixels of an 8x4 block land
+    // on one texel, i.e. when a face covers many more raster pixels than it has texels.  UMR_TEXGRAD_PRE=0|1 forces it.
+    static const int pre_forced = [] {
+        const char* e = getenv("UMR_TEXGRAD_PRE");
+        return e ? (e[0] == '1' ? 1 : 0) : -1;
+    }();
+    const bool tex_pre = pre_forced >= 0 ? pre_forced == 1
+                                         : (double)K.S * K.S >= (grad_faces ? UMR_TEXGRAD_PRE_RATIO_FULL : UMR_TEXGRAD_PRE_RATIO_TEXONLY) *
+                                                                        (double)F * p->texture_size;
     const size_t ntiles = (size_t)grid_pairs.x * grid_pairs.y * B;
     const unsigned list_grid = (unsigned)(ntiles < 444 ? ntiles : 444);  // 3 CTAs x 148 SMs walk the unsaved-tile list
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
@@ -1755,7 +1784,7 @@ extern "C" int umr_raster_backward(const float* face_vertices, const float* text
     if (nc4) {  // 16x16 tiles, softmax, no texture gradient (check_params / above)
         if (pb.cap > 0) {
             count_launch();
-            k_raster_bwd2<1, false, 16, 4><<<grid_pairs, CTA, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, grad_faces,
+            k_raster_bwd2<1, false, 16, 4><<<grid_pairs, BWD2_THREADS, 0, stream>>>(textures, soft_colors, aggrs_info, grad_images, grad_faces,
                                                                             grad_textures, K, pb);
             k_raster_bwd_pairs_list<1, false, 4><<<list_grid, CTA, smem, stream>>>(rec, box, textures, soft_colors, aggrs_info, grad_images,
                                                                                    grad_faces, grad_textures, ubox, K, pb.ctrl + 1,

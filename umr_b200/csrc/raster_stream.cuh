@@ -646,13 +646,22 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
 #define UMR_BWD2_REGPIPE 0
 #endif
 #ifndef UMR_BWD2_CTAS
-#define UMR_BWD2_CTAS 4
+#define UMR_BWD2_CTAS 5   // same-box A/B (profiles/r02_bwd2_cta_ab.txt): 5 CTAs x 256 threads (48 registers) beats 4 x 256 by 5 % at C2 and
+#endif                    // 4 % at 8 x 2048^2; 8-10 CTAs x 128 threads gain up to 8 % on the large render only; 64-thread CTAs lose
+
+#ifndef UMR_BWD2_THREADS
+#define UMR_BWD2_THREADS 256
 #endif
+constexpr int BWD2_THREADS = UMR_BWD2_THREADS, BWD2_WARPS = BWD2_THREADS / 32;  // threads of one k_raster_bwd2 CTA (one tile)
 // TS: side of the forward's tile (16: k_raster_fwd3 / k_raster_fwd2, 32: k_raster_fwd4); one CTA streams one tile
 // GEOM = false: the caller wants no gradient for the vertices (UMR's texture branch renders DETACHED geometry,
 // experiments/train_s2.py:248) -- only the texel gradients are formed, the compiler drops the rest of the arithmetic.
-template <int RGB, bool TEXGRAD, int TS, int NC = 3, bool GEOM = true>  // NC colour channels; pixel planes: g[NC], g_alpha, C[NC], alpha, ssum, smax
-__global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
+// PRE = true: the texel gradients of a step are combined inside the warp before they go to global memory -- lanes that hit
+// the same texel of the step's face (found with match.any) are summed by the lowest of them, which issues the only REDs.
+// Large faces put ~6 pixels of an 8x4 block on one texel: same-address REDs serialise in L2 and were 40 % of this kernel's
+// time at 8 x 2048^2 (profiles/r02_bwd2_cta_ab.txt: 2.9 ms with, 1.7 ms without texture gradient).
+template <int RGB, bool TEXGRAD, int TS, int NC = 3, bool GEOM = true, bool PRE = false>  // NC colour channels; pixel planes: g[NC], g_alpha, C[NC], alpha, ssum, smax
+__global__ void __launch_bounds__(BWD2_THREADS, UMR_BWD2_CTAS) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                         const float* __restrict__ aggrs, const float* __restrict__ grad_images,
                                                         float* __restrict__ grad_faces, float* __restrict__ grad_tex, Consts K,
                                                         PairBuf pb) {
@@ -666,7 +675,7 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
     const int32_t head = __ldg(pb.tile_head + tile_id);
     if (head < 0) return;  // empty, or unsaved (k_raster_bwd_pairs handles it)
     const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
-    for (int pi = tid; pi < NP; pi += CTA) {
+    for (int pi = tid; pi < NP; pi += BWD2_THREADS) {
         const int px = x0 + (pi % TS), py = y0 + (pi / TS);
         const size_t np = (size_t)S * S;
         float v[NV];
@@ -718,7 +727,7 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
     uint32_t seg = (uint32_t)head;
     while (seg != SEG_NONE) {
         const uint32_t NB = __ldg(pb.blk_hdr + seg), next = __ldg(pb.blk_hdr + seg + 1);
-        const uint32_t per = (NB + NWARP - 1) / NWARP;
+        const uint32_t per = (NB + BWD2_WARPS - 1) / BWD2_WARPS;
         const uint32_t kbeg = min(NB, warp * per), kend = min(NB, kbeg + per);
         const uint32_t* hdrs = pb.blk_hdr + seg + 2;
         // The warp streams the records of its block range 32 at a time: blocks are only partly filled (survivors
@@ -801,6 +810,10 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
             if (have_n) load3(act_n, src_n, n0r, n1r, n2r);
             const int f = f_c;
             if (f != cur_f) { flush(); cur_f = f; }
+            int pre_tix = -1;   // PRE: this lane's texel of face f and its NC gradient terms (set below when it contributes)
+            float pre_v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) pre_v[c] = 0.f;
             if (act_c) {
 #if UMR_BWD2_REGPIPE
                 const float4 r0 = c0r, r1 = c1r, r2 = c2r;
@@ -840,8 +853,14 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
                         if (s != 0.f) {
                             const size_t to = ((size_t)f * K.T2 + tix) * NC;
                             if (TEXGRAD) {
+                                if (PRE) {
+                                    pre_tix = tix;
 #pragma unroll
-                                for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
+                                    for (int c = 0; c < NC; ++c) pre_v[c] = s * g[c];
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
+                                }
                             }
                             float Crgb = 0.f;
                             if (GEOM) {
@@ -869,6 +888,33 @@ __global__ void __launch_bounds__(CTA, UMR_BWD2_CTAS) k_raster_bwd2(const float*
                     acc[4] += q * r1.y * sdy;
                     acc[6] += q * r1.z * sdx;
                     acc[7] += q * r1.z * sdy;
+                }
+            }
+            if (PRE && TEXGRAD && RGB == 1) {  // all 32 lanes are here (the stream loop is warp-uniform)
+                const bool has = pre_tix >= 0;
+                if (__any_sync(0xffffffffu, has)) {
+                    const uint32_t lt_ = (1u << lane) - 1u;
+                    const uint32_t pm = __match_any_sync(0xffffffffu, has ? (uint32_t)pre_tix : (0x80000000u | (uint32_t)lane));
+                    const bool leader = (pm & lt_) == 0u;
+                    uint32_t rest = (has && leader) ? (pm & ~(1u << lane)) : 0u;  // the other lanes on this leader's texel
+                    float sum[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) sum[c] = pre_v[c];
+                    while (__any_sync(0xffffffffu, rest != 0u)) {
+                        const int src = rest ? __ffs(rest) - 1 : lane;
+                        const bool take = rest != 0u;
+                        rest &= rest - 1u;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const float t = __shfl_sync(0xffffffffu, pre_v[c], src);
+                            if (take) sum[c] += t;
+                        }
+                    }
+                    if (has && leader) {
+                        float* gt = gtex_img + ((size_t)f * K.T2 + pre_tix) * NC;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) red_add_global(gt + c, sum[c]);
+                    }
                 }
             }
             f_c = f_n; act_c = act_n; src_c = src_n; have = have_n;
