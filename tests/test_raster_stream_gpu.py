@@ -36,9 +36,9 @@ def _run(fv, tex, image_size, rgb, g, cand_per_pixel, tile=0):
 
 @pytest.mark.parametrize("tile", [16, 32])   # k_raster_fwd3 (16x16, static warps) / k_raster_fwd4 (32x32, dynamic pixel blocks)
 @pytest.mark.parametrize("rgb", ["softmax", "hard"])
-# (2, 1, 2, 64): 80 large faces, 4 texels each (51 raster pixels per texel) -> the warp-level texel pre-reduction
+# (2, 1, 1, 64): 80 large faces with one texel each (205 raster pixels per texel) -> the warp-level texel pre-reduction
 # (k_raster_bwd2<..., PRE>) is on
-@pytest.mark.parametrize("B,subdiv,tex_res,image_size", [(2, 3, 3, 64), (1, 3, 6, 128), (1, 2, 2, 37), (2, 1, 2, 64)])
+@pytest.mark.parametrize("B,subdiv,tex_res,image_size", [(2, 3, 3, 64), (1, 3, 6, 128), (1, 2, 2, 37), (2, 1, 1, 64)])
 def test_streamed_backward_matches_recompute_and_oracle(tile, rgb, B, subdiv, tex_res, image_size):
     fv, tex = scene(B, subdiv, tex_res, seed=31 + image_size)
     g = np.random.default_rng(5).normal(size=(B, 4, image_size, image_size)).astype(np.float32)
@@ -201,7 +201,7 @@ def test_four_channel_mode_rejects_what_it_was_not_built_for():
 @pytest.mark.parametrize("tile", [16, 32])
 @pytest.mark.parametrize("rgb", ["softmax", "hard"])
 @pytest.mark.parametrize("cand", [32.0, 0.7])
-@pytest.mark.parametrize("subdiv,tex_res", [(3, 3), (1, 2)])   # (1, 2): large faces -> with the warp-level texel pre-reduction
+@pytest.mark.parametrize("subdiv,tex_res", [(3, 3), (1, 1)])   # (1, 1): large faces -> with the warp-level texel pre-reduction
 def test_texture_only_backward_for_detached_geometry(tile, rgb, cand, subdiv, tex_res):
     """UMR's texture branch renders DETACHED vertices / cameras (experiments/train_s2.py:248): the backward then forms
     only the texel gradients (k_raster_bwd2<..., GEOM = false>) -- same values as the full backward, no grad_faces."""

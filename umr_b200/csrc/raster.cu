@@ -1141,8 +1141,12 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
         if ((float)f == sp[(NV - 1) * NP]) {
             if (TEXGRAD) {
                 float* gt = gtex_img + ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * NC;
+                if (NC == 3) {
+                    red_add3_global(gt, sp[0], sp[NP], sp[2 * NP]);
+                } else {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) red_add_global(gt + c, sp[c * NP]);
+                    for (int c = 0; c < NC; ++c) red_add_global(gt + c, sp[c * NP]);
+                }
             }
         }
     } else if (front || K.double_side) {
@@ -1156,8 +1160,12 @@ __device__ __forceinline__ bool bwd_pair_acc(const float* __restrict__ rc, float
             if (s != 0.f) {
                 const size_t to = ((size_t)f * K.T2 + texel_index(k0, k1, K.R)) * NC;
                 if (TEXGRAD) {
+                    if (NC == 3) {
+                        red_add3_global(gtex_img + to, s * g[0], s * g[1], s * g[2]);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
+                        for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
+                    }
                 }
                 float Crgb = 0.f;
 #pragma unroll
@@ -1496,14 +1504,15 @@ static PairBuf make_pairbuf(const UmrRasterParams* p, int S) {
     return pb;
 }
 
-// raster pixels per texel of the mesh, S^2 / (F * T2), from which the warp-level texel pre-reduction of k_raster_bwd2 is on
-// (same-box A/B, profiles/r02_texgrad_pre_ab.txt: at 91 it saves 9 % of the full and 25 % of the texture-only backward, at 23
-// it costs the full backward 7-17 % and saves the texture-only one 4-13 %, at 6 (C2) it costs both)
+// raster pixels per texel of the mesh, S^2 / (F * T2), from which the warp-level texel pre-reduction of k_raster_bwd2 is on.
+// Same-box A/B with the vector REDs (profiles/r02_texgrad_pre_ab2.txt): it only pays for very large faces -- at 364 it saves
+// 10 % of the full and 18 % of the texture-only backward; at 91 and below (every UMR shape: 6 at C2, 23 at C5, 91 at C3) it
+// costs 6-35 %.
 #ifndef UMR_TEXGRAD_PRE_RATIO_FULL
-#define UMR_TEXGRAD_PRE_RATIO_FULL 48.0
+#define UMR_TEXGRAD_PRE_RATIO_FULL 160.0
 #endif
 #ifndef UMR_TEXGRAD_PRE_RATIO_TEXONLY
-#define UMR_TEXGRAD_PRE_RATIO_TEXONLY 20.0
+#define UMR_TEXGRAD_PRE_RATIO_TEXONLY 120.0
 #endif
 static bool is_generic(const UmrRasterParams* p);
 static int check_params(const UmrRasterParams* p) {

@@ -642,6 +642,17 @@ __global__ void __launch_bounds__(CTA, UMR_FWD2_CTAS) k_raster_fwd2(const float*
 // ---------------------------------------------------------------------------------------------
 // backward: stream the saved pair records of the tile
 // ---------------------------------------------------------------------------------------------
+// NC consecutive texel-gradient floats: RGB goes out as one 2-float vector RED + one scalar (common.cuh)
+template <int NC>
+__device__ __forceinline__ void red_add_texel(float* gt, const float* v) {
+    if (NC == 3) {
+        red_add3_global(gt, v[0], v[1], v[2]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) red_add_global(gt + c, v[c]);
+    }
+}
+
 #ifndef UMR_BWD2_REGPIPE
 #define UMR_BWD2_REGPIPE 0
 #endif
@@ -658,8 +669,8 @@ constexpr int BWD2_THREADS = UMR_BWD2_THREADS, BWD2_WARPS = BWD2_THREADS / 32;  
 // experiments/train_s2.py:248) -- only the texel gradients are formed, the compiler drops the rest of the arithmetic.
 // PRE = true: the texel gradients of a step are combined inside the warp before they go to global memory -- lanes that hit
 // the same texel of the step's face (found with match.any) are summed by the lowest of them, which issues the only REDs.
-// Large faces put ~6 pixels of an 8x4 block on one texel: same-address REDs serialise in L2 and were 40 % of this kernel's
-// time at 8 x 2048^2 (profiles/r02_bwd2_cta_ab.txt: 2.9 ms with, 1.7 ms without texture gradient).
+// Pays only when a face covers hundreds of raster pixels per texel (raster.cu: UMR_TEXGRAD_PRE_RATIO_*); at UMR's shapes the
+// plain vector REDs are faster (profiles/r02_texgrad_pre_ab2.txt).
 template <int RGB, bool TEXGRAD, int TS, int NC = 3, bool GEOM = true, bool PRE = false>  // NC colour channels; pixel planes: g[NC], g_alpha, C[NC], alpha, ssum, smax
 __global__ void __launch_bounds__(BWD2_THREADS, UMR_BWD2_CTAS) k_raster_bwd2(const float* __restrict__ textures, const float* __restrict__ colors_hi,
                                                         const float* __restrict__ aggrs, const float* __restrict__ grad_images,
@@ -839,8 +850,10 @@ __global__ void __launch_bounds__(BWD2_THREADS, UMR_BWD2_CTAS) k_raster_bwd2(con
                     if ((float)f == sp[(NV - 1) * NP]) {  // aggrs[1] = winning face id (:596)
                         if (TEXGRAD) {
                             float* gt = gtex_img + ((size_t)f * K.T2 + tix) * NC;
+                            float g_[NC];
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) red_add_global(gt + c, sp[c * NP]);
+                            for (int c = 0; c < NC; ++c) g_[c] = sp[c * NP];
+                            red_add_texel<NC>(gt, g_);
                         }
                     }
                 } else if (front || K.double_side) {
@@ -858,8 +871,10 @@ __global__ void __launch_bounds__(BWD2_THREADS, UMR_BWD2_CTAS) k_raster_bwd2(con
 #pragma unroll
                                     for (int c = 0; c < NC; ++c) pre_v[c] = s * g[c];
                                 } else {
+                                    float sg[NC];
 #pragma unroll
-                                    for (int c = 0; c < NC; ++c) red_add_global(gtex_img + to + c, s * g[c]);
+                                    for (int c = 0; c < NC; ++c) sg[c] = s * g[c];
+                                    red_add_texel<NC>(gtex_img + to, sg);
                                 }
                             }
                             float Crgb = 0.f;
@@ -912,8 +927,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, UMR_BWD2_CTAS) k_raster_bwd2(con
                     }
                     if (has && leader) {
                         float* gt = gtex_img + ((size_t)f * K.T2 + pre_tix) * NC;
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) red_add_global(gt + c, sum[c]);
+                        red_add_texel<NC>(gt, sum);
                     }
                 }
             }
