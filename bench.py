@@ -252,7 +252,7 @@ class Workload:
             # + 3.0 * texture_dt_loss + 1.0 * TexCycle (visibility from the HARD render, loss_utils.py:327-329)
             #   + 10.0 * CorrLossChamfer on the mean shape (train_s2.py:49-59 weights, :297-316)
             loss = loss + 3.0 * loss_utils.texture_dt_loss(self.flow, dts)
-            _, p2f, aggr = self.hard(verts.detach(), self.faces, cams)
+            p2f, aggr = self.hard.visibility(verts.detach(), self.faces, cams)   # as MultiTextureLoss does (image dropped)
             cyc, _ = self.tex_cycle(self.flow, p2f.detach(), aggr[:, 1].reshape(delta.shape[0], -1).detach())
             head, belly, neck, back = inputs[6:10]
             ms = self.mean_shape[None].expand(delta.shape[0], -1, -1)

@@ -118,6 +118,14 @@ int umr_raster_forward(const float* face_vertices, const float* textures, float*
                        float* soft_colors, float* aggrs_info, float* p2f_info,
                        const UmrRasterParams* params, void* workspace, void* stream);
 
+/* Visibility only: aggrs_info [B,2,S,S] = (depth_min, float(face_index_min)) of the hard z-buffer, bit-identical to what
+ * umr_raster_forward writes with func_id_rgb = UMR_RGB_HARD, without the distance / sigmoid / alpha / colour arithmetic and
+ * without image planes.  This is all the reference keeps of the hard render in MultiTextureLoss (nnutils/loss_utils.py:327-329:
+ * `_, p2f_info, aggr_info = self.hard_renderer(...)`; p2f_info is zero in hard mode, kernel.cu:417-431).  Same params
+ * struct and workspace as umr_raster_forward (UMR's configuration: euclidean / prod / surface). */
+int umr_raster_visibility(const float* face_vertices, float* aggrs_info, const UmrRasterParams* params, void* workspace,
+                          void* stream);
+
 /* Backward.  grad_images [B,4,is,is] is the gradient w.r.t. `images` (the 2x2 pool backward is
  * fused).  Outputs are zero-filled by the call, then accumulated:
  *   grad_faces    [B,F,9]     may be NULL when grad_textures is given: texture-only backward for renders of DETACHED

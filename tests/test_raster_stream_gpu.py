@@ -223,3 +223,17 @@ def test_texture_only_backward_for_detached_geometry(tile, rgb, cand, subdiv, te
                          1e-6 * float(np.abs(full["grad_tex"]).max()) + 1e-7)
     print(msg)
     assert ok, msg
+
+
+@pytest.mark.parametrize("B,subdiv,tex_res,image_size,aa", [(2, 3, 3, 64, True), (1, 2, 2, 37, True), (2, 2, 2, 48, False),
+                                                            (1, 4, 1, 256, True)])
+def test_visibility_only_kernel_equals_the_hard_render(B, subdiv, tex_res, image_size, aa):
+    """k_raster_fwd3<2>: the z-buffer winner per pixel without the image.  Both aggrs planes (depth_min, face_index_min)
+    must be BIT-identical to the full hard render's -- MultiTextureLoss keeps nothing else of it (loss_utils.py:327-329)."""
+    fv, tex = scene(B, subdiv, tex_res, seed=13 + image_size)
+    tfv = torch.from_numpy(fv).to(DEV)
+    _, _, aggr = raster.soft_rasterize(tfv, torch.from_numpy(tex).to(DEV), image_size, aggr_func_rgb="hard", anti_aliasing=aa, **UMR)
+    vis = raster.visibility(tfv, image_size, anti_aliasing=aa, **UMR)
+    assert vis.shape == aggr.shape
+    assert torch.equal(vis, aggr)
+    assert float((vis[:, 1] >= 0).float().mean()) > 0.02   # the mesh is visible somewhere

@@ -32,10 +32,20 @@ class Capture:
             outer.fv.append(fv.detach().cpu().numpy().copy())
             return outer.orig(fv, tex, *a)
         raster.SoftRasterizeFunction.apply = staticmethod(spy)
+        # the visibility-only kernel (MultiTextureLoss's hard render) is a raster call too
+        from umr_b200.soft_renderer import rasterizer as rz
+        self.orig_vis = rz.visibility
+
+        def spy_vis(fv, *a):
+            outer.fv.append(fv.detach().cpu().numpy().copy())
+            return outer.orig_vis(fv, *a)
+        rz.visibility = spy_vis
         return self
 
     def __exit__(self, *exc):
+        from umr_b200.soft_renderer import rasterizer as rz
         raster.SoftRasterizeFunction.apply = self.orig
+        rz.visibility = self.orig_vis
 
 
 def _scene(seed=21):

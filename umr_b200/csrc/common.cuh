@@ -79,6 +79,10 @@ __device__ __forceinline__ void red_add3_global(float* p, float a, float b, floa
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p + (mis ? 0 : 2)), "f"(mis ? a : c) : "memory");
 #endif
 }
+// four floats of a 16-byte aligned slot in ONE reduction (REDG.E.ADD.F32x4)
+__device__ __forceinline__ void red_add4_global(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void red_add_shared(float* addr, float v) {
     asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(addr)), "f"(v) : "memory");
 }

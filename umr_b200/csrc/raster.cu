@@ -1696,6 +1696,43 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
     return (int)cudaGetLastError();
 }
 
+// Visibility only: the hard z-buffer's winner per raster pixel (see k_raster_fwd3<2>).  aggrs_info [B,2,S,S] =
+// (depth_min, float(face_index_min)) exactly as umr_raster_forward writes them with func_id_rgb = UMR_RGB_HARD.
+extern "C" int umr_raster_visibility(const float* face_vertices, float* aggrs_info, const UmrRasterParams* p, void* workspace,
+                                     void* stream_) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!face_vertices || !aggrs_info || !workspace) return UMR_ERR_BAD_ARG;
+    if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
+    if (is_generic(p)) return UMR_ERR_UNSUPPORTED;  // euclidean distance / prod alpha / surface textures: UMR's configuration
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rc = ensure_smem_attrs();
+    if (rc) return rc;
+    const int B = p->batch_size, F = p->num_faces;
+    Consts K = make_consts(p);
+    K.vec_store = (K.aa && (K.S % 8) == 0 && ((uintptr_t)aggrs_info & 15) == 0) ? 1 : 0;
+    const WorkspaceLayout L = ws_layout(B, F, K.S);
+    char* ws = (char*)workspace;
+    float* rec = (float*)(ws + L.rec_off);
+    float4* box = (float4*)(ws + L.box_off);
+    uint32_t* ubox = (uint32_t*)(ws + L.ubox_off);
+    int* ccount = (int*)(ws + L.ccount_off);
+    uint16_t* clist = (uint16_t*)(ws + L.clist_off);
+    cudaError_t e0 = cudaMemsetAsync(ubox, 0, (size_t)B * 4 * sizeof(uint32_t), stream);
+    if (e0 != cudaSuccess) return (int)e0;
+    k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, sqrtf(K.thr));
+    const int ncb = (K.S + CB - 1) / CB;
+    k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
+    const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
+    const PairBuf none{nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
+    if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
+    k_raster_fwd3<2><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, /*textures*/ nullptr, /*images*/ nullptr, /*colors_hi*/ nullptr,
+                                               aggrs_info, /*p2f*/ nullptr, ubox, K, p->eps, 0.f, 0.f, 0.f, none, ncb);
+    if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
+    count_launch(3);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int umr_raster_backward(const float* face_vertices, const float* textures,
                                    const float* soft_colors, const float* aggrs_info,
                                    const float* grad_images, float* grad_faces, float* grad_textures,

@@ -10,6 +10,10 @@
 
 namespace umr {
 
+// RGB: 0 = hard z-buffer colours, 1 = softmax aggregation, 2 = VISIBILITY ONLY -- the winning face of the hard z-buffer
+// (aggrs planes: depth_min, face_index_min) and nothing else: no distance / sigmoid / alpha / colour arithmetic, no image
+// planes.  That is all `MultiTextureLoss` keeps of its hard render (loss_utils.py:327-329: `_, p2f, aggr = hard_renderer(...)`,
+// and p2f is zero in hard mode, kernel.cu:417-431).  Same winner as RGB = 0, bit for bit.
 template <int RGB, int NC = 3>  // NC colour channels (3, or 4: the part-map render of SURVEY.md 8f-2); planes = NC + 1 (alpha)
 #ifndef UMR_FWD3_CTAS
 #define UMR_FWD3_CTAS 4
@@ -22,6 +26,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                                                         Consts K, float eps, float bg0, float bg1, float bg2, PairBuf pb,
                                                         int ncb, float bg3 = 0.f) {
     constexpr int NPL = NC + 1;                                      // image planes: colours + alpha
+    constexpr bool VIS = RGB == 2;
     const float bgc[4] = {bg0, bg1, bg2, bg3};
     constexpr int WG = 16;                                           // list entries per warp group
     __shared__ __align__(128) float s_wrec[NWARP * 2 * WG * REC_F];  // 32 KB: warp-private record stages; reused by the store epilogue
@@ -57,7 +62,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
         if (tid == 0 && pb.cap > 0) pb.tile_head[tile_id] = TILE_EMPTY;
         const float ssum0 = expf(eps / K.gamma);
         float full[NC + 3], g0, g1;
-        if (RGB == 0) {
+        if (RGB != 1) {
 #pragma unroll
             for (int k = 0; k < NC; ++k) full[k] = bgc[k];
             g0 = 10000000.f; g1 = -1.f;
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                     *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - NPL)) * np + off) = val;
                 }
             }
-            if (tid < NPL * 16) {
+            if (!VIS && tid < NPL * 16) {
                 const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
                 float x = pooled[0];
 #pragma unroll
@@ -110,7 +115,8 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) colors_hi[((size_t)b * NPL + k) * np + p] = full[k];
             }
-            if (K.aa) {
+            if (VIS) {
+            } else if (K.aa) {
                 if ((px & 1) == 0 && (py & 1) == 0 && px + 1 < S && py + 1 < S) {
                     const size_t q = (size_t)(py >> 1) * K.IS + (px >> 1);
                     const size_t nq = (size_t)K.IS * K.IS;
@@ -306,7 +312,30 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                 Frag fr;
                 float k0 = 0.f, k1 = 0.f, k2 = 0.f, zsave = 0.f;
                 uint32_t tix = 0, front = 0;
-                if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
+                if (VIS) {
+                    if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
+                        // only a pixel inside the triangle (closed barycentric test, kernel.cu:404) can win the z-buffer
+                        const float w0 = rc[R_INV + 0] * xp + rc[R_INV + 1] * yp + rc[R_INV + 2];
+                        const float w1 = rc[R_INV + 3] * xp + rc[R_INV + 4] * yp + rc[R_INV + 5];
+                        const float w2 = rc[R_INV + 6] * xp + rc[R_INV + 7] * yp + rc[R_INV + 8];
+                        const bool inside = w0 <= 1 && w0 >= 0 && w1 <= 1 && w1 >= 0 && w2 <= 1 && w2 >= 0;
+                        if (inside && (K.double_side || (__float_as_uint(rc[R_FLG]) & 8u))) {
+                            // strictly inside pixels always pass the distance test (kernel.cu:380-383); a barycentric that is
+                            // exactly 0 or 1 takes the reference's outside branch -- evaluate it as the full kernel does
+                            bool pass = w0 > 0 && w1 > 0 && w2 > 0 && w0 < 1 && w1 < 1 && w2 < 1;
+                            if (!pass) pass = fragment(rc, xp, yp, K.thr, K.sigma, fr);
+                            if (pass) {
+                                k0 = w0; k1 = w1; k2 = w2;
+                                clip_bary(k0, k1, k2);
+                                const float zp = depth_of(rc, k0, k1, k2);
+                                if (!(zp < K.near_ || zp > K.far_) && zp < zmin) {
+                                    zmin = zp;
+                                    fid = s_list[jl];
+                                }
+                            }
+                        }
+                    }
+                } else if (live && !(xp > bb.y || xp < bb.x || yp > bb.w || yp < bb.z)) {
                     if (fragment(rc, xp, yp, K.thr, K.sigma, fr)) {
                         acc_a = (float)((double)acc_a * (1. - (double)fr.D));  // kernel.cu:396
                         k0 = fr.w0; k1 = fr.w1; k2 = fr.w2;
@@ -379,9 +408,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                 if (own_w != 0.f) {  // lane r owns the r-th staged face of the group
                     const int e = __fns(m_cur, 0, lane + 1);
                     float* dst = p2f_acc + ((size_t)b * F + s_list[base + e]) * 4;
-                    red_add_global(dst + 0, own_x);
-                    red_add_global(dst + 1, own_y);
-                    red_add_global(dst + 2, own_w);
+                    red_add4_global(dst, own_x, own_y, own_w, 0.f);  // the accumulator slots are 16-byte aligned (ws_layout)
                 }
             }
             __syncwarp();  // every lane is done with stage g & 1 before issue(g + 2) overwrites it
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
     // ---- finalise (kernel.cu:443-475) + fused 2x2 pool + coalesced stores (as round 1) --------------------
     const float alpha = (float)(1. - (double)acc_a);  // kernel.cu:449-451
     float v[NPL], hi[NPL], g0, g1;  // hi: full-resolution planes, v: pooled
-    if (RGB == 0) {
+    if (RGB != 1) {
 #pragma unroll
         for (int k = 0; k < NC; ++k) hi[k] = col[k];
         g0 = zmin; g1 = (float)fid;
@@ -439,7 +466,7 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                 *reinterpret_cast<float4*>(aggrs + ((size_t)b * 2 + (plane - NPL)) * np + off) = val;
             }
         }
-        if (tid < NPL * 16) {
+        if (!VIS && tid < NPL * 16) {
             const int k = tid >> 4, rem = tid & 15, row = rem >> 1, q = rem & 1;
             const float4 val = *reinterpret_cast<const float4*>(st + (NC + 3) * 256 + k * 64 + row * (TILE / 2) + q * 4);
             const int IS = K.IS;
@@ -457,7 +484,8 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
             for (int k = 0; k < NPL; ++k) colors_hi[((size_t)b * NPL + k) * np + p] = hi[k];
         }
     }
-    if (K.aa) {
+    if (VIS) {
+    } else if (K.aa) {
         if (live && (lane & 1) == 0 && (lane & 8) == 0) {
             const int IS = K.IS;
             const size_t q = (size_t)(py >> 1) * IS + (px >> 1);

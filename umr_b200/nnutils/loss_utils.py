@@ -273,7 +273,9 @@ class MultiTextureLoss(nn.Module):
         tex_dt_loss = texture_dt_loss(tex_flow, dts_barrier)
         # visibility map from the HARD renderer; its p2f_info is identically zero (kernel.cu:417-431 is
         # softmax-only) -- reference quirk reproduced
-        _, p2f_info, aggr_info = self.hard_renderer(vs.detach(), fs, proj_cam.detach())
+        # loss_utils.py:327: `_, p2f_info, aggr_info = self.hard_renderer(...)` -- the image is dropped, so only the z-buffer's
+        # winners are computed (visibility-only kernel on CUDA; identical p2f_info / aggr_info)
+        p2f_info, aggr_info = self.hard_renderer.visibility(vs.detach(), fs, proj_cam.detach())
         face_ids = aggr_info[:, 1, :, :].reshape(vs.size(0), -1)
         tex_cycle_loss, _ = self.texture_cycle_fn(tex_flow, p2f_info.detach(), face_ids.detach())
         return tex_loss, tex_dt_loss, tex_cycle_loss, texture_pred

@@ -93,6 +93,21 @@ class SoftRenderer(torch.nn.Module):
                 tex = textures * torch.tensor(c, dtype=torch.float32, device=fv.device)
         return r.rasterizer.rasterize(fv, tex)
 
+    def visibility(self, vertices, faces, cams):
+        """(p2f_info, aggrs_info) of this renderer WITHOUT the image: what `MultiTextureLoss` keeps of its hard render
+        (loss_utils.py:327-329, `_, p2f_info, aggr_info = self.hard_renderer(...)`).  For the hard renderer on CUDA this
+        runs the visibility-only kernel (z-buffer winner per pixel; p2f_info is zero in hard mode, kernel.cu:417-431);
+        every other configuration renders normally and drops the image."""
+        r = self.renderer
+        if self._fusable(vertices) and r.rasterizer.supports_visibility():
+            tr = r.transform.transformer
+            fv, _ = project_faces(vertices.detach(), cams.detach(), faces, offset_z=self.offset_z, eye_z=float(tr._eye[2]),
+                                  viewing_scale=tr.viewing_scale, flip_y=True, light=None)
+            aggrs = r.rasterizer.visibility(fv)
+            return torch.zeros(fv.shape[0], fv.shape[1], 2, device=fv.device, dtype=torch.float32), aggrs
+        _, p2f, aggrs = self.forward(vertices, faces, cams)
+        return p2f, aggrs
+
     def forward(self, vertices, faces, cams, textures=None):
         """vertices [B,V,3], faces [B,F,3], cams [B,7], textures [B,F,T2,3] | None, as the reference (smr.py:80-87).
         Extension: `cams` may hold H camera hypotheses per mesh -- cams [B*H,7] with vertices / faces

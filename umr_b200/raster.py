@@ -286,3 +286,30 @@ def soft_rasterize(face_vertices, textures, image_size=256, background_color=(0,
     return SoftRasterizeFunction.apply(face_vertices, textures, image_size, background_color, near, far,
                                        fill_back, eps, sigma_val, dist_func, dist_eps, gamma_val,
                                        aggr_func_rgb, aggr_func_alpha, texture_type, anti_aliasing)
+
+
+def visibility(face_vertices, image_size=256, near=1, far=100, fill_back=True, eps=1e-3, sigma_val=1e-5,
+               dist_eps=1e-4, gamma_val=1e-4, anti_aliasing=False):
+    """The hard z-buffer's winner per raster pixel and nothing else: returns aggrs_info [B,2,S,S] = (depth_min,
+    float(face_index_min)), bit-identical to `soft_rasterize(..., aggr_func_rgb="hard")[2]` (euclidean / prod / surface
+    configuration), without the distance / sigmoid / alpha / colour arithmetic and without image planes.  It is all the
+    reference keeps of the hard render in MultiTextureLoss (nnutils/loss_utils.py:327-329).  No gradient (the reference
+    detaches its inputs there)."""
+    if not face_vertices.is_cuda:
+        raise TypeError("Rasterize module supports only cuda Tensors")  # soft_rasterize.py:117-118
+    lib = _lib.load()
+    dev = face_vertices.device
+    B, F = face_vertices.shape[:2]
+    fv = face_vertices.detach().reshape(B, F, 9).contiguous().float()
+    S = int(image_size) * (2 if anti_aliasing else 1)
+    params = make_params(B, F, 1, image_size, anti_aliasing, (0, 0, 0), near, far, fill_back, eps, sigma_val, "euclidean",
+                         dist_eps, gamma_val, "hard", "prod", "surface")
+    _attach_events(params, "fwd")
+    with torch.cuda.device(dev):
+        aggrs = torch.empty(B, 2, S, S, device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.umr_raster_workspace_bytes(B, F, int(image_size), params.anti_aliasing), device=dev,
+                         dtype=torch.uint8)
+        rc = lib.umr_raster_visibility(_ptr(fv), _ptr(aggrs), ctypes.byref(params), _ptr(ws), _stream_ptr(dev))
+    _lib.check(rc, "umr_raster_visibility")
+    params.ev_kernel_start = params.ev_kernel_stop = None
+    return aggrs

@@ -2,7 +2,7 @@
 and error messages); the 2x supersampling + `avg_pool2d` of rasterizer.py:43,52-53 is fused into the kernels."""
 import torch.nn as nn
 
-from ..raster import soft_rasterize
+from ..raster import soft_rasterize, visibility
 from ._args import bind
 
 # (name, default) in the reference's positional order
@@ -35,6 +35,16 @@ class SoftRasterizer(nn.Module):
     def rasterize(self, face_vertices, face_textures):
         """Rasterise raster-space face vertices [B,F,3,3] with face textures [B,F,T2,3]."""
         return soft_rasterize(face_vertices, face_textures, *[getattr(self, k) for k in KERNEL_ARGS])
+
+    def supports_visibility(self):
+        """The visibility-only kernel exists for UMR's configuration of the hard renderer (nnutils/smr.py:52-58)."""
+        return (self.dist_func == "euclidean" and self.aggr_func_alpha == "prod" and self.texture_type == "surface"
+                and self.aggr_func_rgb == "hard")
+
+    def visibility(self, face_vertices):
+        """aggrs_info [B,2,S,S] of the hard z-buffer (depth_min, face_index_min) without rendering the image."""
+        return visibility(face_vertices, self.image_size, self.near, self.far, self.fill_back, self.eps, self.sigma_val,
+                          self.dist_eps, self.gamma_val, self.anti_aliasing)
 
     def forward(self, mesh, mode=None):
         return self.rasterize(mesh.face_vertices, mesh.face_textures)
