@@ -252,8 +252,8 @@ class Workload:
             # + 3.0 * texture_dt_loss + 1.0 * TexCycle (visibility from the HARD render, loss_utils.py:327-329)
             #   + 10.0 * CorrLossChamfer on the mean shape (train_s2.py:49-59 weights, :297-316)
             loss = loss + 3.0 * loss_utils.texture_dt_loss(self.flow, dts)
-            p2f, aggr = self.hard.visibility(verts.detach(), self.faces, cams)   # as MultiTextureLoss does (image dropped)
-            cyc, _ = self.tex_cycle(self.flow, p2f.detach(), aggr[:, 1].reshape(delta.shape[0], -1).detach())
+            p2f, visible = self.hard.visible_faces(verts.detach(), self.faces, cams)   # as MultiTextureLoss does (image dropped)
+            cyc, _ = self.tex_cycle(self.flow, p2f, None, visible=visible)
             head, belly, neck, back = inputs[6:10]
             ms = self.mean_shape[None].expand(delta.shape[0], -1, -1)
             corr, _ = self.corr(head, belly, back, neck, ms, cams)   # (argument order as train_s2.py:311 passes them)

@@ -122,9 +122,12 @@ int umr_raster_forward(const float* face_vertices, const float* textures, float*
  * umr_raster_forward writes with func_id_rgb = UMR_RGB_HARD, without the distance / sigmoid / alpha / colour arithmetic and
  * without image planes.  This is all the reference keeps of the hard render in MultiTextureLoss (nnutils/loss_utils.py:327-329:
  * `_, p2f_info, aggr_info = self.hard_renderer(...)`; p2f_info is zero in hard mode, kernel.cu:417-431).  Same params
- * struct and workspace as umr_raster_forward (UMR's configuration: euclidean / prod / surface). */
-int umr_raster_visibility(const float* face_vertices, float* aggrs_info, const UmrRasterParams* params, void* workspace,
-                          void* stream);
+ * struct and workspace as umr_raster_forward (UMR's configuration: euclidean / prod / surface).
+ * visible_faces [B,F] u8 (optional): 1 where the face wins at least one pixel (a background pixel marks face F-1, as the
+ * reference's negative index does) -- the set TexCycle extracts from the plane with torch.unique (loss_utils.py:161-166); hand it to umr_texcycle_forward(face_ids = NULL, visible = ...).  aggrs_info
+ * may then be NULL: no plane is written at all. */
+int umr_raster_visibility(const float* face_vertices, float* aggrs_info, uint8_t* visible_faces,
+                          const UmrRasterParams* params, void* workspace, void* stream);
 
 /* Backward.  grad_images [B,4,is,is] is the gradient w.r.t. `images` (the 2x2 pool backward is
  * fused).  Outputs are zero-filled by the call, then accumulated:

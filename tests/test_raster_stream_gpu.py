@@ -237,3 +237,21 @@ def test_visibility_only_kernel_equals_the_hard_render(B, subdiv, tex_res, image
     assert vis.shape == aggr.shape
     assert torch.equal(vis, aggr)
     assert float((vis[:, 1] >= 0).float().mean()) > 0.02   # the mesh is visible somewhere
+
+
+@pytest.mark.parametrize("B,subdiv,image_size,aa", [(2, 3, 64, True), (1, 2, 37, True), (2, 2, 48, False)])
+def test_visible_face_bytes_equal_the_set_in_the_face_index_plane(B, subdiv, image_size, aa):
+    """want_faces: the [B,F] bytes are exactly the faces present in the hard render's face-index plane, with the
+    reference's quirk that a background pixel (-1) marks face F-1 (loss_utils.py:161-166 index with the raw plane)."""
+    fv, tex = scene(B, subdiv, 2, seed=3 + image_size)
+    tfv = torch.from_numpy(fv).to(DEV)
+    F = fv.shape[1]
+    _, _, aggr = raster.soft_rasterize(tfv, torch.from_numpy(tex).to(DEV), image_size, aggr_func_rgb="hard", anti_aliasing=aa, **UMR)
+    mask = raster.visibility(tfv, image_size, anti_aliasing=aa, want_faces=True, **UMR)
+    assert mask.dtype == torch.uint8 and tuple(mask.shape) == (B, F)
+    want = torch.zeros(B, F, dtype=torch.uint8)
+    for b in range(B):
+        ids = torch.unique(aggr[b, 1].long().cpu())
+        want[b, ids] = 1          # -1 -> F-1, like the reference's indexing
+    assert torch.equal(mask.cpu(), want)
+    assert 0 < int(want.sum()) < B * F

@@ -36,9 +36,9 @@ class Capture:
         from umr_b200.soft_renderer import rasterizer as rz
         self.orig_vis = rz.visibility
 
-        def spy_vis(fv, *a):
+        def spy_vis(fv, *a, **kw):
             outer.fv.append(fv.detach().cpu().numpy().copy())
-            return outer.orig_vis(fv, *a)
+            return outer.orig_vis(fv, *a, **kw)
         rz.visibility = spy_vis
         return self
 

@@ -567,16 +567,18 @@ extern "C" int umr_chamfer_backward(const float* a, const float* b, const int32_
 
 extern "C" int umr_texcycle_forward(const float* flow, const float* prob, const float* face_ids, uint8_t* visible,
                                     float* loss, int32_t B, int32_t F, int32_t T2, int64_t P, void* stream_) {
-    if (!flow || !prob || !face_ids || !visible || !loss || B <= 0 || F <= 0 || T2 <= 0 || P <= 0)
-        return UMR_ERR_BAD_ARG;
+    // face_ids == NULL: `visible` was already filled by umr_raster_visibility (its visible_faces output)
+    if (!flow || !prob || !visible || !loss || B <= 0 || F <= 0 || T2 <= 0 || (face_ids && P <= 0)) return UMR_ERR_BAD_ARG;
     if (B > 65535) return UMR_ERR_TOO_LARGE;
     cudaStream_t st = (cudaStream_t)stream_;
-    cudaError_t e = cudaMemsetAsync(visible, 0, (size_t)B * F, st);
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(loss, 0, sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
-    const int64_t blocks = (P / 4 + 255) / 256 + 1;
-    count_launch(); k_visible<<<dim3((unsigned)(blocks > 1024 ? 1024 : blocks), B), 256, 0, st>>>(face_ids, visible, F, P);
+    if (face_ids) {
+        e = cudaMemsetAsync(visible, 0, (size_t)B * F, st);
+        if (e != cudaSuccess) return (int)e;
+        const int64_t blocks = (P / 4 + 255) / 256 + 1;
+        count_launch(); k_visible<<<dim3((unsigned)(blocks > 1024 ? 1024 : blocks), B), 256, 0, st>>>(face_ids, visible, F, P);
+    }
     const int n = B * F;
     const float scale = 1.f / ((float)n * 2.f);  // MSELoss mean over B*F*2 elements
     count_launch(); k_texcycle_fwd<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(flow),

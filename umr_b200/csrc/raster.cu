@@ -1698,11 +1698,11 @@ extern "C" int umr_raster_forward(const float* face_vertices, const float* textu
 
 // Visibility only: the hard z-buffer's winner per raster pixel (see k_raster_fwd3<2>).  aggrs_info [B,2,S,S] =
 // (depth_min, float(face_index_min)) exactly as umr_raster_forward writes them with func_id_rgb = UMR_RGB_HARD.
-extern "C" int umr_raster_visibility(const float* face_vertices, float* aggrs_info, const UmrRasterParams* p, void* workspace,
-                                     void* stream_) {
+extern "C" int umr_raster_visibility(const float* face_vertices, float* aggrs_info, uint8_t* visible_faces,
+                                     const UmrRasterParams* p, void* workspace, void* stream_) {
     int rc = check_params(p);
     if (rc) return rc;
-    if (!face_vertices || !aggrs_info || !workspace) return UMR_ERR_BAD_ARG;
+    if (!face_vertices || (!aggrs_info && !visible_faces) || !workspace) return UMR_ERR_BAD_ARG;
     if (((uintptr_t)workspace & 255) != 0) return UMR_ERR_BAD_ARG;
     if (is_generic(p)) return UMR_ERR_UNSUPPORTED;  // euclidean distance / prod alpha / surface textures: UMR's configuration
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -1720,6 +1720,10 @@ extern "C" int umr_raster_visibility(const float* face_vertices, float* aggrs_in
     uint16_t* clist = (uint16_t*)(ws + L.clist_off);
     cudaError_t e0 = cudaMemsetAsync(ubox, 0, (size_t)B * 4 * sizeof(uint32_t), stream);
     if (e0 != cudaSuccess) return (int)e0;
+    if (visible_faces) {
+        e0 = cudaMemsetAsync(visible_faces, 0, (size_t)B * F, stream);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
     k_prep<<<dim3((F + 255) / 256, B), 256, 0, stream>>>(face_vertices, rec, box, ubox, F, sqrtf(K.thr));
     const int ncb = (K.S + CB - 1) / CB;
     k_bin_coarse<<<dim3(ncb, ncb, B), CTA, (size_t)(F < BOX_PIECE ? F : BOX_PIECE) * 16, stream>>>(box, ubox, clist, ccount, F, K.S);
@@ -1727,7 +1731,8 @@ extern "C" int umr_raster_visibility(const float* face_vertices, float* aggrs_in
     const PairBuf none{nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
     k_raster_fwd3<2><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, /*textures*/ nullptr, /*images*/ nullptr, /*colors_hi*/ nullptr,
-                                               aggrs_info, /*p2f*/ nullptr, ubox, K, p->eps, 0.f, 0.f, 0.f, none, ncb);
+                                               aggrs_info, /*p2f*/ nullptr, ubox, K, p->eps, 0.f, 0.f, 0.f, none, ncb, 0.f,
+                                               visible_faces);
     if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
     count_launch(3);
     return (int)cudaGetLastError();

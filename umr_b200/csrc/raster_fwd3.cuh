@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                                                         float* __restrict__ colors_hi, float* __restrict__ aggrs,
                                                         float* __restrict__ p2f_acc, const uint32_t* __restrict__ ubox,
                                                         Consts K, float eps, float bg0, float bg1, float bg2, PairBuf pb,
-                                                        int ncb, float bg3 = 0.f) {
+                                                        int ncb, float bg3 = 0.f,
+                                                        uint8_t* __restrict__ vis_mask = nullptr) {  // RGB = 2: optional [B,F] "face is visible" bytes; aggrs may be NULL
     constexpr int NPL = NC + 1;                                      // image planes: colours + alpha
     constexpr bool VIS = RGB == 2;
     const float bgc[4] = {bg0, bg1, bg2, bg3};
@@ -57,6 +58,15 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
     const int nc = tile_outside_union(ubox, b, s_ext) ? 0 : __ldg(ccount + cidx);
 
     if (nc == 0) {
+        if (VIS) {
+            // background pixels carry face id -1, which the reference's indexing turns into "face F-1 is visible"
+            // (loss_utils.py:161-166); reproduced like k_visible does
+            if (vis_mask != nullptr && tid == 0) {
+                uint8_t* m = vis_mask + (size_t)b * F + (F - 1);
+                if (*reinterpret_cast<volatile uint8_t*>(m) == 0) *m = 1;
+            }
+            if (aggrs == nullptr) return;  // no planes wanted (uniform)
+        }
         // ---- untouched tile (most of the image): every pixel holds the initial state.  Same arithmetic as the
         // general path (kernel.cu:335-348, 443-475), evaluated once, stored with 128-bit stores where possible.
         if (tid == 0 && pb.cap > 0) pb.tile_head[tile_id] = TILE_EMPTY;
@@ -421,6 +431,15 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
 
     // ---- finalise (kernel.cu:443-475) + fused 2x2 pool + coalesced stores (as round 1) --------------------
     const float alpha = (float)(1. - (double)acc_a);  // kernel.cu:449-451
+    if (VIS) {
+        // face-visibility bytes (what TexCycle derives from the face-index plane with torch.unique, loss_utils.py:161-166):
+        // test before set -- a stale 0 only repeats the store
+        if (vis_mask != nullptr && live) {
+            uint8_t* m = vis_mask + (size_t)b * F + (fid >= 0 ? fid : F - 1);  // -1 (background) marks face F-1, see above
+            if (*reinterpret_cast<volatile uint8_t*>(m) == 0) *m = 1;
+        }
+        if (aggrs == nullptr) return;  // uniform
+    }
     float v[NPL], hi[NPL], g0, g1;  // hi: full-resolution planes, v: pooled
     if (RGB != 1) {
 #pragma unroll

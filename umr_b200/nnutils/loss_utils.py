@@ -146,10 +146,15 @@ class TexCycle(nn.Module):
     def __init__(self, im_size=256, nf=1280, eps=1e-12):
         super().__init__()
 
-    def forward(self, flow, prob, aggr_info):
+    def forward(self, flow, prob, aggr_info, visible=None):
+        """`visible` (extension): the [B,F] uint8 face-visibility bytes of `SoftRenderer.visible_faces`, used instead of
+        scanning `aggr_info` (which may then be None)."""
         nb, nf = flow.size(0), flow.size(1)
         flow_grid = flow.reshape(nb, nf, -1, 2)
-        loss = ops.tex_cycle(flow_grid, prob, aggr_info.reshape(nb, -1))
+        if visible is not None:
+            loss = ops.tex_cycle(flow_grid, prob, None, visible)
+        else:
+            loss = ops.tex_cycle(flow_grid, prob, aggr_info.reshape(nb, -1))
         # second output is for visualisation only in the reference (:181-182)
         avg_flow_vis = flow_grid[0, 0:10].mean(dim=1)
         return loss, avg_flow_vis
@@ -275,9 +280,14 @@ class MultiTextureLoss(nn.Module):
         # softmax-only) -- reference quirk reproduced
         # loss_utils.py:327: `_, p2f_info, aggr_info = self.hard_renderer(...)` -- the image is dropped, so only the z-buffer's
         # winners are computed (visibility-only kernel on CUDA; identical p2f_info / aggr_info)
-        p2f_info, aggr_info = self.hard_renderer.visibility(vs.detach(), fs, proj_cam.detach())
-        face_ids = aggr_info[:, 1, :, :].reshape(vs.size(0), -1)
-        tex_cycle_loss, _ = self.texture_cycle_fn(tex_flow, p2f_info.detach(), face_ids.detach())
+        vis = self.hard_renderer.visible_faces(vs.detach(), fs, proj_cam.detach())
+        if vis is not None:   # CUDA: the visibility kernel hands TexCycle the visible-face bytes directly (no plane at all)
+            p2f_info, visible = vis
+            tex_cycle_loss, _ = self.texture_cycle_fn(tex_flow, p2f_info, None, visible=visible)
+        else:
+            p2f_info, aggr_info = self.hard_renderer.visibility(vs.detach(), fs, proj_cam.detach())
+            face_ids = aggr_info[:, 1, :, :].reshape(vs.size(0), -1)
+            tex_cycle_loss, _ = self.texture_cycle_fn(tex_flow, p2f_info.detach(), face_ids.detach())
         return tex_loss, tex_dt_loss, tex_cycle_loss, texture_pred
 
 

@@ -108,6 +108,19 @@ class SoftRenderer(torch.nn.Module):
         _, p2f, aggrs = self.forward(vertices, faces, cams)
         return p2f, aggrs
 
+    def visible_faces(self, vertices, faces, cams):
+        """(p2f_info, visible [B,F] uint8) -- the set of faces TexCycle extracts from the hard render's face-index plane
+        (loss_utils.py:161-166), computed by the visibility kernel itself so that no plane is written or re-read.
+        None when this renderer / device has no visibility kernel (callers then use `visibility` / `forward`)."""
+        r = self.renderer
+        if not (self._fusable(vertices) and r.rasterizer.supports_visibility()):
+            return None
+        tr = r.transform.transformer
+        fv, _ = project_faces(vertices.detach(), cams.detach(), faces, offset_z=self.offset_z, eye_z=float(tr._eye[2]),
+                              viewing_scale=tr.viewing_scale, flip_y=True, light=None)
+        mask = r.rasterizer.visibility(fv, want_faces=True)
+        return torch.zeros(fv.shape[0], fv.shape[1], 2, device=fv.device, dtype=torch.float32), mask
+
     def forward(self, vertices, faces, cams, textures=None):
         """vertices [B,V,3], faces [B,F,3], cams [B,7], textures [B,F,T2,3] | None, as the reference (smr.py:80-87).
         Extension: `cams` may hold H camera hypotheses per mesh -- cams [B*H,7] with vertices / faces

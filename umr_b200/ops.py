@@ -265,19 +265,25 @@ def dist_chamfer(a, b):
 # texture cycle
 # -------------------------------------------------------------------------------------------------
 class TexCycleFunction(torch.autograd.Function):
-    """flow [B,F,T2,2], prob [B,F,2], face_ids [B,P] (float plane, -1 = background) -> scalar loss."""
+    """flow [B,F,T2,2], prob [B,F,2], face_ids [B,P] (float plane, -1 = background) -> scalar loss.
+    `visible` [B,F] uint8 (from raster.visibility(..., want_faces=True)) replaces the scan of the plane."""
 
     @staticmethod
-    def forward(ctx, flow, prob, face_ids):
-        _need_cuda(flow, prob, face_ids)
+    def forward(ctx, flow, prob, face_ids, visible=None):
+        _need_cuda(flow, prob) if face_ids is None else _need_cuda(flow, prob, face_ids)
         lib = _lib.load()
         fl = flow.detach().contiguous().float()
         pr = prob.detach().contiguous().float()
-        ids = face_ids.detach().contiguous().float()
         B, F, T2 = fl.shape[0], fl.shape[1], fl.shape[2]
-        P = ids.shape[1]
+        if visible is not None:
+            if visible.dtype != torch.uint8 or tuple(visible.shape) != (B, F) or not visible.is_cuda:
+                raise ValueError("visible must be a CUDA uint8 tensor of shape [B,F]")
+            ids, P = None, 0
+        else:
+            ids = face_ids.detach().contiguous().float()
+            P = ids.shape[1]
         with torch.cuda.device(fl.device):
-            vis = torch.empty(B, F, device=fl.device, dtype=torch.uint8)
+            vis = visible.contiguous() if visible is not None else torch.empty(B, F, device=fl.device, dtype=torch.uint8)
             loss = torch.empty(1, device=fl.device, dtype=torch.float32)
             rc = lib.umr_texcycle_forward(_ptr(fl), _ptr(pr), _ptr(ids), _ptr(vis), _ptr(loss), B, F, T2, P,
                                           _stream_ptr(fl.device))
@@ -296,11 +302,11 @@ class TexCycleFunction(torch.autograd.Function):
             rc = lib.umr_texcycle_backward(_ptr(fl), _ptr(pr), _ptr(vis), _ptr(g), _ptr(gflow), B, F, T2,
                                            _stream_ptr(fl.device))
         _lib.check(rc, "umr_texcycle_backward")
-        return gflow, None, None
+        return gflow, None, None, None
 
 
-def tex_cycle(flow, prob, face_ids):
-    return TexCycleFunction.apply(flow, prob, face_ids)
+def tex_cycle(flow, prob, face_ids=None, visible=None):
+    return TexCycleFunction.apply(flow, prob, face_ids, visible)
 
 
 # -------------------------------------------------------------------------------------------------

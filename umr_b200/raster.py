@@ -289,12 +289,15 @@ def soft_rasterize(face_vertices, textures, image_size=256, background_color=(0,
 
 
 def visibility(face_vertices, image_size=256, near=1, far=100, fill_back=True, eps=1e-3, sigma_val=1e-5,
-               dist_eps=1e-4, gamma_val=1e-4, anti_aliasing=False):
+               dist_eps=1e-4, gamma_val=1e-4, anti_aliasing=False, want_faces=False):
     """The hard z-buffer's winner per raster pixel and nothing else: returns aggrs_info [B,2,S,S] = (depth_min,
     float(face_index_min)), bit-identical to `soft_rasterize(..., aggr_func_rgb="hard")[2]` (euclidean / prod / surface
     configuration), without the distance / sigmoid / alpha / colour arithmetic and without image planes.  It is all the
     reference keeps of the hard render in MultiTextureLoss (nnutils/loss_utils.py:327-329).  No gradient (the reference
-    detaches its inputs there)."""
+    detaches its inputs there).
+
+    want_faces=True returns instead the [B,F] uint8 "face wins at least one pixel" bytes TexCycle derives from the plane
+    (a background pixel marks face F-1, like the reference's negative index) and writes no plane at all."""
     if not face_vertices.is_cuda:
         raise TypeError("Rasterize module supports only cuda Tensors")  # soft_rasterize.py:117-118
     lib = _lib.load()
@@ -306,10 +309,11 @@ def visibility(face_vertices, image_size=256, near=1, far=100, fill_back=True, e
                          dist_eps, gamma_val, "hard", "prod", "surface")
     _attach_events(params, "fwd")
     with torch.cuda.device(dev):
-        aggrs = torch.empty(B, 2, S, S, device=dev, dtype=torch.float32)
+        aggrs = None if want_faces else torch.empty(B, 2, S, S, device=dev, dtype=torch.float32)
+        faces = torch.empty(B, F, device=dev, dtype=torch.uint8) if want_faces else None
         ws = torch.empty(lib.umr_raster_workspace_bytes(B, F, int(image_size), params.anti_aliasing), device=dev,
                          dtype=torch.uint8)
-        rc = lib.umr_raster_visibility(_ptr(fv), _ptr(aggrs), ctypes.byref(params), _ptr(ws), _stream_ptr(dev))
+        rc = lib.umr_raster_visibility(_ptr(fv), _ptr(aggrs), _ptr(faces), ctypes.byref(params), _ptr(ws), _stream_ptr(dev))
     _lib.check(rc, "umr_raster_visibility")
     params.ev_kernel_start = params.ev_kernel_stop = None
-    return aggrs
+    return faces if want_faces else aggrs

@@ -41,10 +41,11 @@ class SoftRasterizer(nn.Module):
         return (self.dist_func == "euclidean" and self.aggr_func_alpha == "prod" and self.texture_type == "surface"
                 and self.aggr_func_rgb == "hard")
 
-    def visibility(self, face_vertices):
-        """aggrs_info [B,2,S,S] of the hard z-buffer (depth_min, face_index_min) without rendering the image."""
+    def visibility(self, face_vertices, want_faces=False):
+        """aggrs_info [B,2,S,S] of the hard z-buffer (depth_min, face_index_min) without rendering the image; or, with
+        want_faces, only the [B,F] uint8 "face is visible" bytes."""
         return visibility(face_vertices, self.image_size, self.near, self.far, self.fill_back, self.eps, self.sigma_val,
-                          self.dist_eps, self.gamma_val, self.anti_aliasing)
+                          self.dist_eps, self.gamma_val, self.anti_aliasing, want_faces)
 
     def forward(self, mesh, mode=None):
         return self.rasterize(mesh.face_vertices, mesh.face_textures)
