@@ -15,6 +15,7 @@
  *   umr_iou_forward / _backward      replace nnutils/loss_utils.py:41-48 (`neg_iou_loss`).
  *   umr_chamfer_forward / _backward  replace nnutils/chamfer_python.py:43-64 (`distChamfer`).
  *   umr_texcycle_forward / _backward replace nnutils/loss_utils.py:152-182 (`TexCycle.forward`).
+ *   umr_corr_chamfer_forward / _backward replace nnutils/loss_utils.py:218-248 (`CorrLossChamfer.forward`).
  *
  * Conventions: plain device pointers + sizes, no torch types.  Every buffer is CALLER-allocated
  * (torch owns all memory); the library keeps no global mutable state and is re-entrant across host
@@ -233,6 +234,26 @@ int umr_chamfer_backward(const float* a, const float* b, const int32_t* idx_ab,
                          const int32_t* idx_ba, const float* grad_dist_ab,
                          const float* grad_dist_ba, float* grad_a, float* grad_b, int32_t B,
                          int32_t N, int32_t M, int32_t D, void* stream);
+
+/* CorrLossChamfer (nnutils/loss_utils.py:194-248; call site experiments/train_s2.py:300-315) fused: project the NS selected
+ * part vertices (`selection` [NS] int32 = head | belly | neck | back indices concatenated, `part_ends` [4] their cumulative
+ * counts, loss_utils.py:211-216) with the render's camera (orthographic_proj_withz(...)[:, :, :2], geom_utils.py:74-91),
+ * squared distance of every projected vertex to the nearest of its part's targets (targets[g] [B, target_counts[g], 2];
+ * the `dist1` of distChamfer, chamfer_python.py:43-64, in the defined fp32 order of umr_chamfer_forward), times weights[g],
+ * mean over the NS vertices (loss_utils.py:232-239).  vertices [B,V,3] with `vertices_batch_stride` elements between renders
+ * (0 = one mesh shared by all renders, e.g. the mean shape).  Outputs: vert2d [B,NS,2], nearest [B,NS] int32, loss [B].
+ * The four `targets` pointers / counts / ends / weights are HOST arrays of length 4.
+ * Backward: grad_loss [B], optional grad_vert2d [B,NS,2] -> grad_vertices [B,V,3] (zero-filled by the call; may be NULL) and
+ * grad_cams [B,7] (may be NULL).  Targets receive no gradient (they are data in the reference). */
+int umr_corr_chamfer_forward(const float* vertices, int64_t vertices_batch_stride, const float* cams,
+                             const int32_t* selection, const float* const* targets, const int32_t* target_counts,
+                             const int32_t* part_ends, const float* weights, float* vert2d, int32_t* nearest,
+                             float* loss, int32_t B, int32_t NS, void* stream);
+int umr_corr_chamfer_backward(const float* vertices, int64_t vertices_batch_stride, const float* cams,
+                              const int32_t* selection, const float* const* targets, const int32_t* target_counts,
+                              const int32_t* part_ends, const float* weights, const float* vert2d,
+                              const int32_t* nearest, const float* grad_loss, const float* grad_vert2d,
+                              float* grad_vertices, float* grad_cams, int32_t B, int32_t NS, int32_t V, void* stream);
 
 /* TexCycle (loss_utils.py:152-182).  flow [B,F,T2,2], prob [B,F,2], face_ids [B,P] (the hard
  * renderer's aggrs_info[:,1] plane as float, -1 = background which marks face F-1 visible like the

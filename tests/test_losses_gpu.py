@@ -174,3 +174,49 @@ def test_fused_loss_head_equals_the_two_reference_losses(B, H):
     y = rgba.to(DEV)
     unfused = 2.5 * loss_utils.neg_iou_loss(y[:, 3], mgt.to(DEV)) + 3.0 * loss_utils.texture_loss_masks(y[:, :3], gt.to(DEV), mgt.to(DEV), y[:, 3])
     _chk("fused vs unfused", got, unfused, 1e-5, 1e-7)
+
+
+@pytest.mark.parametrize("avg", [True, False])
+@pytest.mark.parametrize("shared_mesh", [False, True])
+def test_fused_corr_loss_chamfer_equals_the_composition(avg, shared_mesh):
+    """csrc/vertex.cu k_corr_fwd / k_corr_bwd vs the module's torch composition (project_points + 4 x distChamfer + cat +
+    mean, loss_utils.py:218-248 -- itself checked against the CPU oracle in test_train_step_gpu.py): same loss, projected
+    vertices, and gradients for the vertices (also through an expanded one-mesh view) and the cameras."""
+    import numpy as np
+    from umr_b200 import synth
+    from umr_b200.nnutils import loss_utils
+    rng = np.random.default_rng(17)
+    B, IS = 6, 64
+    v, f = synth.icosphere(3)
+    V = v.shape[0]
+    parts = [torch.from_numpy(p) for p in synth.part_vertex_sets(rng, V, sizes=(20, 40, 20, 40))]
+    pts = [torch.from_numpy(p).to(DEV) for p in synth.part_points(rng, B)]
+    m = loss_utils.CorrLossChamfer(None, IS, part_vertices=parts)
+    m.weights = [1, 1, 0.5, 0.25]          # exercise all four parts (the reference's [1, 1, 0, 0] zeroes two of them)
+    base = torch.from_numpy(synth.bird_like(v, rng, B))
+    cams0 = torch.from_numpy(synth.cameras(rng, B))
+    outs = []
+    for fused in (True, False):
+        cams = cams0.clone().to(DEV).requires_grad_(True)
+        if shared_mesh:
+            leaf = base[0].clone().to(DEV).requires_grad_(True)
+            verts = leaf[None].expand(B, -1, -1)
+        else:
+            leaf = base.clone().to(DEV).requires_grad_(True)
+            verts = leaf
+        if not fused:
+            m.renderer.proj_fn = lambda X, cam, offset_z=0.: loss_utils.geom_utils.orthographic_proj_withz(X, cam, offset_z)
+        out = m(pts[0], pts[1], pts[2], pts[3], verts, cams, avg=avg)
+        if avg:
+            loss, v2d = out
+            (loss + 0.01 * v2d.sum()).backward()
+        else:
+            loss, v2d = out, None
+            (loss * torch.linspace(0.5, 1.5, B, device=DEV)).sum().backward()
+        outs.append((loss.detach().cpu(), None if v2d is None else v2d.detach().cpu(), leaf.grad.cpu(), cams.grad.cpu()))
+    (l1, v1, gv1, gc1), (l0, v0, gv0, gc0) = outs
+    assert torch.allclose(l1, l0, rtol=1e-5, atol=1e-7)
+    if v1 is not None:
+        assert torch.equal(v1, v0)      # same projection arithmetic, bit for bit
+    assert torch.allclose(gv1, gv0, rtol=1e-4, atol=1e-6 * float(gv0.abs().max()))
+    assert torch.allclose(gc1, gc0, rtol=1e-4, atol=1e-5 * float(gc0.abs().max()))

@@ -57,6 +57,14 @@ EXPORTS = {
                                                          ctypes.c_void_p]),
     "umr_raster_visibility": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.POINTER(UmrRasterParams), ctypes.c_void_p,
                                              ctypes.c_void_p]),
+    "umr_corr_chamfer_forward": (ctypes.c_int, [c_f32p, ctypes.c_int64, c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                                ctypes.POINTER(ctypes.c_float), c_f32p, ctypes.c_void_p, c_f32p, ctypes.c_int32,
+                                                ctypes.c_int32, ctypes.c_void_p]),
+    "umr_corr_chamfer_backward": (ctypes.c_int, [c_f32p, ctypes.c_int64, c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                                 ctypes.POINTER(ctypes.c_float), c_f32p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p,
+                                                 c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     "umr_project_faces_forward": (ctypes.c_int, [c_f32p] * 5 + [ctypes.POINTER(UmrProjectParams), ctypes.c_void_p]),
     "umr_project_faces_backward": (ctypes.c_int, [c_f32p] * 8 + [ctypes.POINTER(UmrProjectParams), ctypes.c_void_p]),
     "umr_bilinear_sample_forward": (ctypes.c_int, [c_f32p] * 3 + [ctypes.c_int32] * 5 + [ctypes.c_void_p]),

@@ -257,6 +257,143 @@ __global__ void __launch_bounds__(256) k_project_backward(const float* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CorrLossChamfer (nnutils/loss_utils.py:194-248) in one kernel per direction.  The reference projects the selected part
+// vertices with ~60 tiny torch kernels (quaternion products through stack / cat), runs distChamfer once per part (bmm +
+// min), concatenates and averages; its backward is ~150 more launches including a radix sort for the index_put.  Here one
+// CTA per render: project the NS selected vertices (same arithmetic as k_project_faces: quat_rotate, scale, translate),
+// nearest target of the vertex's own part in the defined fp32 order of k_chamfer_nn (losses.cu), weighted mean.
+// ---------------------------------------------------------------------------------------------
+struct CorrCfg {
+    const float* tgt[4];   // [B, m[g], 2] target points of part g
+    int m[4];              // target counts
+    int end[4];            // exclusive end of part g in the concatenated vertex selection (loss_utils.py:211-216 `nums`)
+    float w[4];            // per-part weights (loss_utils.py:210: [1, 1, 0, 0])
+};
+
+__device__ __forceinline__ int corr_part(const CorrCfg& c, int j) { return j < c.end[0] ? 0 : (j < c.end[1] ? 1 : (j < c.end[2] ? 2 : 3)); }
+
+__global__ void __launch_bounds__(256) k_corr_fwd(const float* __restrict__ verts, int64_t verts_bstride, const float* __restrict__ cams,
+                                                  const int32_t* __restrict__ sel, CorrCfg c, float* __restrict__ vert2d,
+                                                  int32_t* __restrict__ nn, float* __restrict__ loss, int NS) {
+    __shared__ float s_part[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Cam k = load_cam(cams, b);
+    float acc = 0.f;  // meaningful in lane 0
+    for (int j = warp; j < NS; j += 8) {
+        const float* p = verts + (size_t)b * verts_bstride + (size_t)__ldg(sel + j) * 3;
+        float r1, r2, r3;
+        quat_rotate(k, __ldg(p), __ldg(p + 1), __ldg(p + 2), r1, r2, r3);
+        const float qx = k.s * r1 + k.tx, qy = k.s * r2 + k.ty;   // orthographic_proj_withz(...)[:, :, :2] (geom_utils.py:74-91)
+        const int g = corr_part(c, j);
+        const float* tb = c.tgt[g] + (size_t)b * c.m[g] * 2;
+        const float qq = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
+        float best = __int_as_float(0x7f800000);
+        int bi = 0x7fffffff;
+        for (int t = lane; t < c.m[g]; t += 32) {
+            const float kx = __ldg(tb + 2 * t), ky = __ldg(tb + 2 * t + 1);
+            const float kk = __fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky));
+            const float zz = __fadd_rn(__fmul_rn(qx, kx), __fmul_rn(qy, ky));
+            const float P = __fsub_rn(__fadd_rn(qq, kk), __fmul_rn(2.f, zz));  // chamfer_python.py:63, as k_chamfer_nn
+            if (P < best) { best = P; bi = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            vert2d[((size_t)b * NS + j) * 2 + 0] = qx;
+            vert2d[((size_t)b * NS + j) * 2 + 1] = qy;
+            nn[(size_t)b * NS + j] = bi;
+            acc += best * c.w[g];   // d_to_target * weight (loss_utils.py:236)
+        }
+    }
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_part[w];   // fixed order: deterministic
+        loss[b] = t / (float)NS;                      // torch.mean(torch.cat(terms, 1), 1) (:239)
+    }
+}
+
+// per-vertex backward of r = quat_rotate(q, X); p = s r + t given G = dL/dp (dL/dpz = gz): adds to gc[7] (scale, tx, ty, q0..q3)
+// and returns dL/dX (the derivation of k_project_backward).
+__device__ __forceinline__ void project_point_backward(const Cam& k, float X, float Y, float Z, float gx, float gy, float gz,
+                                                       float* gc, float& o0, float& o1, float& o2) {
+    float r1, r2, r3;
+    quat_rotate(k, X, Y, Z, r1, r2, r3);
+    gc[0] += gx * r1 + gy * r2 + gz * r3;
+    gc[1] += gx;
+    gc[2] += gy;
+    const float Gx = k.s * gx, Gy = k.s * gy, Gz = k.s * gz;
+    const float vx = k.q1, vy = k.q2, vz = k.q3, q0 = k.q0;
+    const float vv = vx * vx + vy * vy + vz * vz;
+    const float vG = vx * Gx + vy * Gy + vz * Gz;
+    const float vX = vx * X + vy * Y + vz * Z;
+    const float XG = X * Gx + Y * Gy + Z * Gz;
+    const float c0 = q0 * q0 - vv;
+    const float cx = vy * Gz - vz * Gy, cy = vz * Gx - vx * Gz, cz = vx * Gy - vy * Gx;  // v x G
+    o0 = c0 * Gx + 2.f * vG * vx - 2.f * q0 * cx;
+    o1 = c0 * Gy + 2.f * vG * vy - 2.f * q0 * cy;
+    o2 = c0 * Gz + 2.f * vG * vz - 2.f * q0 * cz;
+    const float wx = vy * Z - vz * Y, wy = vz * X - vx * Z, wz = vx * Y - vy * X;  // v x X
+    gc[3] += 2.f * (q0 * XG + (Gx * wx + Gy * wy + Gz * wz));
+    const float ex = Y * Gz - Z * Gy, ey = Z * Gx - X * Gz, ez = X * Gy - Y * Gx;  // X x G
+    gc[4] += 2.f * (-XG * vx + vG * X + vX * Gx + q0 * ex);
+    gc[5] += 2.f * (-XG * vy + vG * Y + vX * Gy + q0 * ey);
+    gc[6] += 2.f * (-XG * vz + vG * Z + vX * Gz + q0 * ez);
+}
+
+// backward: grad_loss [B] (per render), optional grad_vert2d [B,NS,2] -> grad_verts [B,V,3] (zero-filled by the host,
+// atomics: a vertex may sit in several parts) and grad_cams [B,7].  Targets are constants (the reference's are data).
+__global__ void __launch_bounds__(256) k_corr_bwd(const float* __restrict__ verts, int64_t verts_bstride, const float* __restrict__ cams,
+                                                  const int32_t* __restrict__ sel, CorrCfg c, const float* __restrict__ vert2d,
+                                                  const int32_t* __restrict__ nn, const float* __restrict__ grad_loss,
+                                                  const float* __restrict__ grad_vert2d, float* __restrict__ gverts,
+                                                  float* __restrict__ gcams, int NS, int V) {
+    __shared__ float s[8][7];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Cam k = load_cam(cams, b);
+    const float gl = __ldg(grad_loss + b) / (float)NS;
+    float gc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int j = threadIdx.x; j < NS; j += 256) {
+        const int g = corr_part(c, j);
+        const int vi = __ldg(sel + j);
+        const float* p = verts + (size_t)b * verts_bstride + (size_t)vi * 3;
+        const float qx = __ldg(vert2d + ((size_t)b * NS + j) * 2), qy = __ldg(vert2d + ((size_t)b * NS + j) * 2 + 1);
+        const float* t = c.tgt[g] + ((size_t)b * c.m[g] + __ldg(nn + (size_t)b * NS + j)) * 2;
+        const float gd = gl * c.w[g];
+        // d/dq of (|q|^2 + |t|^2 - 2 q.t) = 2 q - 2 t (chamfer_python.py:63; the argmin is piecewise constant)
+        float gx = gd * (2.f * qx - 2.f * __ldg(t)), gy = gd * (2.f * qy - 2.f * __ldg(t + 1));
+        if (grad_vert2d != nullptr) {
+            gx += __ldg(grad_vert2d + ((size_t)b * NS + j) * 2);
+            gy += __ldg(grad_vert2d + ((size_t)b * NS + j) * 2 + 1);
+        }
+        float o0, o1, o2;
+        project_point_backward(k, __ldg(p), __ldg(p + 1), __ldg(p + 2), gx, gy, 0.f, gc, o0, o1, o2);
+        if (gverts != nullptr) {
+            float* o = gverts + ((size_t)b * V + vi) * 3;
+            atomicAdd(o, o0); atomicAdd(o + 1, o1); atomicAdd(o + 2, o2);
+        }
+    }
+    if (gcams == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const float r = warp_sum(gc[i]);
+        if (lane == 0) s[warp][i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        float r = 0.f;
+        for (int w = 0; w < 8; ++w) r += s[w][threadIdx.x];
+        gcams[(size_t)b * 7 + threadIdx.x] = r;   // one CTA per render: plain store
+    }
+}
+
 }  // namespace umr
 
 using namespace umr;
@@ -316,5 +453,53 @@ extern "C" int umr_project_faces_backward(const float* vertices, const float* ca
                                                                    make_lc(p));
     k_project_backward<<<dim3((V + 255) / 256, B), 256, 0, st>>>(vertices, cams, grad_proj, grad_vertices, grad_cams, V, H,
                                                                  make_pc(p));
+    return (int)cudaGetLastError();
+}
+
+static int make_corr_cfg(CorrCfg& c, const float* const* targets, const int32_t* target_counts, const int32_t* part_ends,
+                         const float* weights, int NS) {
+    int prev = 0;
+    for (int g = 0; g < 4; ++g) {
+        if (!targets[g] || target_counts[g] <= 0 || part_ends[g] < prev) return UMR_ERR_BAD_ARG;
+        c.tgt[g] = targets[g]; c.m[g] = target_counts[g]; c.end[g] = part_ends[g]; c.w[g] = weights[g];
+        prev = part_ends[g];
+    }
+    return prev == NS ? UMR_OK : UMR_ERR_BAD_ARG;
+}
+
+extern "C" int umr_corr_chamfer_forward(const float* vertices, int64_t vertices_batch_stride, const float* cams,
+                                        const int32_t* selection, const float* const* targets, const int32_t* target_counts,
+                                        const int32_t* part_ends, const float* weights, float* vert2d, int32_t* nearest,
+                                        float* loss, int32_t B, int32_t NS, void* stream_) {
+    if (!vertices || !cams || !selection || !targets || !target_counts || !part_ends || !weights || !vert2d || !nearest ||
+        !loss || B <= 0 || NS <= 0)
+        return UMR_ERR_BAD_ARG;
+    CorrCfg c;
+    const int rc = make_corr_cfg(c, targets, target_counts, part_ends, weights, NS);
+    if (rc) return rc;
+    count_launch();
+    k_corr_fwd<<<B, 256, 0, (cudaStream_t)stream_>>>(vertices, vertices_batch_stride, cams, selection, c, vert2d, nearest, loss, NS);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int umr_corr_chamfer_backward(const float* vertices, int64_t vertices_batch_stride, const float* cams,
+                                         const int32_t* selection, const float* const* targets, const int32_t* target_counts,
+                                         const int32_t* part_ends, const float* weights, const float* vert2d,
+                                         const int32_t* nearest, const float* grad_loss, const float* grad_vert2d,
+                                         float* grad_vertices, float* grad_cams, int32_t B, int32_t NS, int32_t V, void* stream_) {
+    if (!vertices || !cams || !selection || !targets || !target_counts || !part_ends || !weights || !vert2d || !nearest ||
+        !grad_loss || B <= 0 || NS <= 0 || V <= 0)
+        return UMR_ERR_BAD_ARG;
+    CorrCfg c;
+    const int rc = make_corr_cfg(c, targets, target_counts, part_ends, weights, NS);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (grad_vertices) {
+        cudaError_t e = cudaMemsetAsync(grad_vertices, 0, (size_t)B * V * 3 * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    count_launch();
+    k_corr_bwd<<<B, 256, 0, st>>>(vertices, vertices_batch_stride, cams, selection, c, vert2d, nearest, grad_loss, grad_vert2d,
+                                  grad_vertices, grad_cams, NS, V);
     return (int)cudaGetLastError();
 }

@@ -197,6 +197,16 @@ class CorrLossChamfer(nn.Module):
         groups = (self.head_vertices, self.belly_vertices, self.neck_vertices, self.back_vertices)
         targets = (head_points, belly_points, neck_points, back_points)
         idx = self._index_on(verts.device)
+        if verts.is_cuda and self.renderer.proj_fn is geom_utils.orthographic_proj_withz:
+            # one fused kernel per direction (csrc/vertex.cu k_corr_fwd / k_corr_bwd) instead of the ~250 launches of the
+            # composition below: projection, per-part nearest target, weights, mean
+            cache = self.__dict__.setdefault("_idx32_cache", {})
+            if str(verts.device) not in cache:
+                cache[str(verts.device)] = idx.to(torch.int32)
+            loss, vert2d = ops.corr_chamfer(verts, cams, cache[str(verts.device)], targets, self.nums, self.weights)
+            if avg:
+                return torch.mean(loss), vert2d
+            return loss
         vert2d = self.renderer.project_points(verts[:, idx, :], cams)  # [B, sum(sizes), 2]
         terms, start = [], 0
         for group, target, weight in zip(groups, targets, self.weights):

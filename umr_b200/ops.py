@@ -425,3 +425,74 @@ def load_textures(image, faces_uv, textures, is_update):
                                _stream_ptr(textures.device))
     _lib.check(rc, "umr_load_textures")
     return textures
+
+
+# -------------------------------------------------------------------------------------------------
+# CorrLossChamfer fused (nnutils/loss_utils.py:218-248)
+# -------------------------------------------------------------------------------------------------
+class CorrChamferFunction(torch.autograd.Function):
+    """verts [B,V,3] (or [1,V,3] / an expanded view: one mesh for all renders), cams [B,7], selection [NS] int32 (the four
+    parts' vertex indices concatenated), targets = 4 tensors [B,m_g,2], part_ends (4 cumulative counts), weights (4 floats)
+    -> (loss [B], vert2d [B,NS,2]).  One kernel per direction instead of ~250 torch launches."""
+
+    @staticmethod
+    def _cfg(targets, part_ends, weights):
+        tp = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in targets])
+        tc = (ctypes.c_int32 * 4)(*[int(t.shape[1]) for t in targets])
+        pe = (ctypes.c_int32 * 4)(*[int(e) for e in part_ends])
+        wt = (ctypes.c_float * 4)(*[float(w) for w in weights])
+        return tp, tc, pe, wt
+
+    @staticmethod
+    def forward(ctx, verts, cams, selection, t0, t1, t2, t3, part_ends, weights):
+        _need_cuda(verts, cams, selection, t0, t1, t2, t3)
+        lib = _lib.load()
+        B = cams.shape[0]
+        shared = verts.shape[0] == 1 or (verts.dim() == 3 and verts.stride(0) == 0)   # one mesh for every render
+        vv = (verts[:1] if shared else verts).detach().contiguous().float()
+        if not shared and vv.shape[0] != B:
+            raise ValueError("verts batch %d does not match cams batch %d" % (vv.shape[0], B))
+        V = vv.shape[1]
+        cc = cams.detach().contiguous().float()
+        targets = [t.detach().contiguous().float() for t in (t0, t1, t2, t3)]
+        for t in targets:
+            if t.dim() != 3 or t.shape[0] != B or t.shape[2] != 2:
+                raise ValueError("part targets must be [B, m, 2]")
+        sel = selection if selection.dtype == torch.int32 else selection.to(torch.int32)
+        NS = int(sel.numel())
+        with torch.cuda.device(vv.device):
+            vert2d = torch.empty(B, NS, 2, device=vv.device, dtype=torch.float32)
+            nn = torch.empty(B, NS, device=vv.device, dtype=torch.int32)
+            loss = torch.empty(B, device=vv.device, dtype=torch.float32)
+            tp, tc, pe, wt = CorrChamferFunction._cfg(targets, part_ends, weights)
+            rc = lib.umr_corr_chamfer_forward(_ptr(vv), 0 if shared else V * 3, _ptr(cc), _ptr(sel), tp, tc, pe, wt, _ptr(vert2d),
+                                              _ptr(nn), _ptr(loss), B, NS, _stream_ptr(vv.device))
+        _lib.check(rc, "umr_corr_chamfer_forward")
+        ctx.save_for_backward(vv, cc, sel, vert2d, nn, *targets)
+        ctx.cfg = (tuple(int(e) for e in part_ends), tuple(float(w) for w in weights), shared, tuple(verts.shape))
+        return loss, vert2d
+
+    @staticmethod
+    def backward(ctx, g_loss, g_v2d):
+        lib = _lib.load()
+        vv, cc, sel, vert2d, nn = ctx.saved_tensors[:5]
+        targets = list(ctx.saved_tensors[5:])
+        part_ends, weights, shared, vshape = ctx.cfg
+        B, NS, V = cc.shape[0], vert2d.shape[1], vv.shape[1]
+        gl = g_loss.contiguous().float() if g_loss is not None else torch.zeros(B, device=cc.device)
+        gv2 = g_v2d.contiguous().float() if g_v2d is not None else None
+        with torch.cuda.device(vv.device):
+            gverts = torch.empty(B, V, 3, device=vv.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+            gcams = torch.empty(B, 7, device=vv.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+            tp, tc, pe, wt = CorrChamferFunction._cfg(targets, part_ends, weights)
+            rc = lib.umr_corr_chamfer_backward(_ptr(vv), 0 if shared else V * 3, _ptr(cc), _ptr(sel), tp, tc, pe, wt, _ptr(vert2d),
+                                               _ptr(nn), _ptr(gl), _ptr(gv2), _ptr(gverts), _ptr(gcams), B, NS, V,
+                                               _stream_ptr(vv.device))
+        _lib.check(rc, "umr_corr_chamfer_backward")
+        if gverts is not None and shared and vshape[0] == 1:
+            gverts = gverts.sum(0, keepdim=True)   # a [1,V,3] input broadcast here; an expanded [B,V,3] view gets the per-render
+        return (gverts, gcams) + (None,) * 7      # gradients and autograd's expand-backward sums them
+
+
+def corr_chamfer(verts, cams, selection, targets, part_ends, weights):
+    return CorrChamferFunction.apply(verts, cams, selection, *targets, part_ends, weights)
