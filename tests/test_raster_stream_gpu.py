@@ -239,11 +239,21 @@ def test_visibility_only_kernel_equals_the_hard_render(B, subdiv, tex_res, image
     assert float((vis[:, 1] >= 0).float().mean()) > 0.02   # the mesh is visible somewhere
 
 
-@pytest.mark.parametrize("B,subdiv,image_size,aa", [(2, 3, 64, True), (1, 2, 37, True), (2, 2, 48, False)])
-def test_visible_face_bytes_equal_the_set_in_the_face_index_plane(B, subdiv, image_size, aa):
-    """want_faces: the [B,F] bytes are exactly the faces present in the hard render's face-index plane, with the
-    reference's quirk that a background pixel (-1) marks face F-1 (loss_utils.py:161-166 index with the raw plane)."""
+@pytest.mark.parametrize("slivers", [False, True])
+@pytest.mark.parametrize("B,subdiv,image_size,aa", [(2, 3, 64, True), (1, 2, 37, True), (2, 2, 48, False), (2, 3, 512, True),
+                                                    (1, 4, 256, True)])
+def test_visible_face_bytes_equal_the_set_in_the_face_index_plane(B, subdiv, image_size, aa, slivers):
+    """want_faces (k_visible_faces: face-parallel z-buffer per 64x64 bin): the [B,F] bytes are exactly the faces present in
+    the hard render's face-index plane, with the reference's quirk that a background pixel (-1) marks face F-1
+    (loss_utils.py:161-166 index with the raw plane).  `slivers` flattens every 7th face to a needle / a zero-area
+    triangle: those take the whole-cull-box scan (R_FLG bit 4)."""
     fv, tex = scene(B, subdiv, 2, seed=3 + image_size)
+    if slivers:
+        fv = fv.copy().reshape(B, -1, 3, 3)
+        t = np.float32(1e-6)
+        fv[:, ::7, 2, :2] = (fv[:, ::7, 0, :2] + fv[:, ::7, 1, :2]) * np.float32(0.5) + t       # needle
+        fv[:, ::21, 2] = fv[:, ::21, 1]                                                         # two coincident corners
+        fv = np.ascontiguousarray(fv.reshape(B, -1, 9))
     tfv = torch.from_numpy(fv).to(DEV)
     F = fv.shape[1]
     _, _, aggr = raster.soft_rasterize(tfv, torch.from_numpy(tex).to(DEV), image_size, aggr_func_rgb="hard", anti_aliasing=aa, **UMR)
@@ -253,5 +263,6 @@ def test_visible_face_bytes_equal_the_set_in_the_face_index_plane(B, subdiv, ima
     for b in range(B):
         ids = torch.unique(aggr[b, 1].long().cpu())
         want[b, ids] = 1          # -1 -> F-1, like the reference's indexing
-    assert torch.equal(mask.cpu(), want)
+    diff = (mask.cpu() != want).nonzero()
+    assert diff.numel() == 0, "faces differing: %s" % diff[:10].tolist()
     assert 0 < int(want.sum()) < B * F

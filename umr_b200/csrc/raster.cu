@@ -131,6 +131,18 @@ __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ fv, floa
     else if ((x2 - x1) * (x0 - x1) + (y2 - y1) * (y0 - y1) < 0) flags = 2;
     else if ((x0 - x2) * (x1 - x2) + (y0 - y2) * (y1 - y2) < 0) flags = 4;
     if ((y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0)) flags |= 8;  // kernel.cu:42-44
+    {
+        // bit 4: thin / degenerate triangle (sine of its smallest angle below ~1e-3): its barycentric inverse is not
+        // trustworthy, so "inside" may be claimed far from the triangle.  Only k_visible_faces reads
+        // it -- such faces are scanned over their whole cull box there instead of the tight bounding box.
+        const float l01 = (x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0);
+        const float l02 = (x2 - x0) * (x2 - x0) + (y2 - y0) * (y2 - y0);
+        const float l12 = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
+        const float lmin = fminf(fminf(l01, l02), l12);
+        const float prod2 = (l01 * l02 * l12) / fmaxf(lmin, 1e-30f);   // product of the two longest squared edges
+        const float draw = x2 * (y0 - y1) + x0 * (y1 - y2) + x1 * (y2 - y0);
+        if (!(draw * draw >= 1e-6f * prod2)) flags |= 16u;               // also NaN / zero area
+    }
     out[R_FLG] = __uint_as_float(flags);
     out[R_IZ2 + 0] = 1.f / (v[2] * v[2]);
     out[R_IZ2 + 1] = 1.f / (v[5] * v[5]);
@@ -1730,9 +1742,16 @@ extern "C" int umr_raster_visibility(const float* face_vertices, float* aggrs_in
     const dim3 grid((K.S + TILE - 1) / TILE, (K.S + TILE - 1) / TILE, B);
     const PairBuf none{nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
     if (p->ev_kernel_start) cudaEventRecord((cudaEvent_t)p->ev_kernel_start, stream);
-    k_raster_fwd3<2><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, /*textures*/ nullptr, /*images*/ nullptr, /*colors_hi*/ nullptr,
-                                               aggrs_info, /*p2f*/ nullptr, ubox, K, p->eps, 0.f, 0.f, 0.f, none, ncb, 0.f,
-                                               visible_faces);
+    static const bool pixel_only = [] {  // UMR_VISIBILITY_IMPL=pixel keeps the per-pixel kernel for the bytes too (A/B testing)
+        const char* e = getenv("UMR_VISIBILITY_IMPL");
+        return e && e[0] == 'p';
+    }();
+    if (visible_faces && !aggrs_info && !pixel_only)   // only the visible-face bytes: face-parallel z-buffer per 64x64 bin
+        k_visible_faces<<<dim3(ncb, ncb, B), CTA, 0, stream>>>(rec, clist, ccount, visible_faces, K);
+    else
+        k_raster_fwd3<2><<<grid, CTA, 0, stream>>>(rec, box, clist, ccount, /*textures*/ nullptr, /*images*/ nullptr,
+                                                   /*colors_hi*/ nullptr, aggrs_info, /*p2f*/ nullptr, ubox, K, p->eps, 0.f, 0.f, 0.f,
+                                                   none, ncb, 0.f, visible_faces);
     if (p->ev_kernel_stop) cudaEventRecord((cudaEvent_t)p->ev_kernel_stop, stream);
     count_launch(3);
     return (int)cudaGetLastError();
