@@ -70,6 +70,20 @@ def main():
     tex_leaf = tex.detach().clone().requires_grad_(True)
     img_t, _, _ = r2(verts.detach(), faces, cams.detach(), tex_leaf)
     total = total + img_t[:, :3].mean()
+    # visibility kernels (MultiTextureLoss's hard render): per-pixel planes, face-parallel visible-face bytes -> TexCycle
+    rh = smr.SoftRenderer(IS, "hard")
+    _, aggr_v = rh.visibility(verts, faces, cams)
+    p2f_v, vis_bytes = rh.visible_faces(verts, faces, cams)
+    assert aggr_v.shape[1] == 2 and vis_bytes.dtype == torch.uint8
+    cyc2, _ = loss_utils.TexCycle()(flow, p2f_v, None, visible=vis_bytes)
+    total = total + cyc2
+    # fused CorrLossChamfer (projection + per-part nearest target + mean), also through a one-mesh expanded view
+    pv = [torch.from_numpy(p) for p in synth.part_vertex_sets(rng, v.shape[0], sizes=(5, 9, 5, 9))]
+    pp = [torch.from_numpy(p).to(dev) for p in synth.part_points(rng, B)]
+    corr_fn = loss_utils.CorrLossChamfer(None, IS, part_vertices=pv)
+    c1, _ = corr_fn(pp[0], pp[1], pp[2], pp[3], verts, cams)
+    c2 = corr_fn(pp[0], pp[1], pp[2], pp[3], verts[:1].expand(B, -1, -1), cams, avg=False)
+    total = total + c1 + c2.sum()
     fcpu = torch.from_numpy(f.astype(np.int64))
     total = total + 1e-3 * sr.LaplacianLoss(torch.from_numpy(v), fcpu).to(dev)(verts).sum() \
         + 1e-3 * sr.FlattenLoss(fcpu).to(dev)(verts).sum()

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(CTA) k_visible_faces(const float* __restrict__
     for (int i = warp; i < nc; i += NWARP) {
         const int f = __ldg(cl + i);
         const float* rc = rec_img + (size_t)f * REC_F;
+        if (lane == 0 && i + NWARP < nc)   // the warp's next face: pull its 128-byte record into L1 while this one is scanned
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_img + (size_t)__ldg(cl + i + NWARP) * REC_F));
         const uint32_t flg = __float_as_uint(__ldg(rc + R_FLG));
         if (!(K.double_side || (flg & 8u))) continue;   // back face of a single-sided render never wins (warp-uniform)
         // pixel rectangle to test: bounding box of the vertices widened by 2 pixels (an inside pixel lies in the box; the
