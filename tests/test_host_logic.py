@@ -328,3 +328,44 @@ def test_regulariser_cpu_formulas_match_the_reference_restatement():
     assert torch.equal(rec, dense)
     ft = sr.FlattenLoss(faces).edge_table
     assert ft.shape[1] == 4 and ft.dtype == torch.int32 and ft.shape[0] == 3 * f.shape[0] // 2
+
+
+def test_round2_extensions_reject_cpu_tensors_and_keep_the_cpu_paths():
+    """The CUDA-only extensions (visibility kernels, 4-channel part maps, fused CorrLossChamfer) must fail loudly on CPU
+    tensors -- there is no CPU fallback in the product -- while the modules' generic torch paths stay usable."""
+    from umr_b200 import ops, raster
+    fv = torch.zeros(1, 4, 9)
+    with pytest.raises(TypeError):
+        raster.visibility(fv, 16)
+    with pytest.raises(TypeError):
+        raster.visibility(fv, 16, want_faces=True)
+    with pytest.raises(TypeError):
+        ops.tex_cycle(torch.zeros(1, 4, 4, 2), torch.zeros(1, 4, 2), None, torch.zeros(1, 4, dtype=torch.uint8))
+    with pytest.raises(TypeError):
+        ops.corr_chamfer(torch.zeros(1, 8, 3), torch.zeros(1, 7), torch.zeros(4, dtype=torch.int32),
+                         [torch.zeros(1, 2, 2)] * 4, (1, 2, 3, 4), (1, 1, 0, 0))
+    r = smr.SoftRenderer(16, "hard")
+    assert r.visible_faces(torch.zeros(1, 8, 3), torch.zeros(1, 4, 3, dtype=torch.long), torch.zeros(1, 7)) is None
+    assert r.renderer.rasterizer.supports_visibility()
+    assert not smr.SoftRenderer(16, "softmax").renderer.rasterizer.supports_visibility()
+    # part_matching_loss keeps the reference-shaped buffers and adds ONE batch-shared 4-channel texture
+    one_hot = torch.zeros(1, 6, 4, 5)
+    one_hot[..., 2] = 1
+    m = loss_utils.part_matching_loss(None, None, 0, im_size=16, batch_size=2, tex_size=2, stex_one_hot=one_hot)
+    assert tuple(m.stex_parts.shape) == (1, 6, 4, 4) and tuple(m.stex1.shape) == (2, 6, 4, 3)
+    assert float(m.stex_parts[..., 1].min()) == 1.0 and float(m.stex_parts[..., 0].max()) == 0.0
+    assert "stex_parts" not in m.state_dict()          # not part of the reference's state
+
+
+def test_launch_list_tool_finds_the_step_in_the_committed_log(capsys):
+    """tools/launch_list.py on the committed ncu launch log of a C2 step."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import launch_list
+    launch_list.main(os.path.join(root, "profiles", "r02_launches_C2_step.csv"))
+    out = capsys.readouterr().out
+    assert "one eager step = " in out and "k_raster_fwd3" in out and "k_raster_bwd2" in out
+    share = [l for l in out.splitlines() if "k_raster_fwd3" in l and "%" in l]
+    assert share and float(share[0].split("us")[1].split("%")[0]) > 40.0
