@@ -16,7 +16,7 @@ namespace umr {
 // and p2f is zero in hard mode, kernel.cu:417-431).  Same winner as RGB = 0, bit for bit.
 template <int RGB, int NC = 3>  // NC colour channels (3, or 4: the part-map render of SURVEY.md 8f-2); planes = NC + 1 (alpha)
 #ifndef UMR_FWD3_CTAS
-#define UMR_FWD3_CTAS 4
+#define UMR_FWD3_CTAS 4   // same-box A/B at C2: 3 CTAs (80 registers) and 5 CTAs (48 registers, 88 B of spills: 0.461 vs 0.386 ms) both lose
 #endif
 __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float* __restrict__ rec_all, const float4* __restrict__ box_all,
                                                         const uint16_t* __restrict__ clist, const int* __restrict__ ccount,
