@@ -15,6 +15,9 @@ namespace umr {
 // planes.  That is all `MultiTextureLoss` keeps of its hard render (loss_utils.py:327-329: `_, p2f, aggr = hard_renderer(...)`,
 // and p2f is zero in hard mode, kernel.cu:417-431).  Same winner as RGB = 0, bit for bit.
 template <int RGB, int NC = 3>  // NC colour channels (3, or 4: the part-map render of SURVEY.md 8f-2); planes = NC + 1 (alpha)
+#ifndef UMR_FWD3_POS_TABLE
+#define UMR_FWD3_POS_TABLE 0   // 1: rank table instead of __fns in issue() -- built, awaiting a same-box A/B
+#endif
 #ifndef UMR_FWD3_CTAS
 #define UMR_FWD3_CTAS 4   // same-box A/B at C2: 3 CTAs (80 registers) and 5 CTAs (48 registers, 88 B of spills: 0.461 vs 0.386 ms) both lose
 #endif
@@ -40,6 +43,9 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
     __shared__ uint32_t s_warp_blk[NWARP];
     __shared__ uint32_t s_segbase;
     __shared__ int s_save;
+#if UMR_FWD3_POS_TABLE
+    __shared__ uint8_t s_pos[NWARP][WG];      // list offset of the r-th face of the warp's current issue mask
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
@@ -292,12 +298,25 @@ __global__ void __launch_bounds__(CTA, UMR_FWD3_CTAS) k_raster_fwd3(const float*
                 const int base = g * WG;
                 m = __ballot_sync(0xffffffffu, lane < WG && base + lane < n && (s_meet[min(base + lane, n - 1)] & wbit));
                 const int cntm = __popc(m);
+#if UMR_FWD3_POS_TABLE
+                // rank -> list offset through a 16-byte per-warp table (the find-n-th-set-bit intrinsic is a software loop:
+                // 2.7 % of this kernel's instructions, profiles/r02_raster_fwd3_C2_ncu_summary.txt)
+                if ((m >> lane) & 1u) s_pos[warp][__popc(m & lt)] = (uint8_t)lane;
+                __syncwarp();
+#endif
                 for (int r = lane >> 3; r < cntm; r += 4) {
+#if UMR_FWD3_POS_TABLE
+                    const int e = s_pos[warp][r];
+#else
                     const int e = __fns(m, 0, r + 1);  // list offset of the r-th face this warp needs
+#endif
                     const int f = s_list[base + e];
                     cp_async16(wst + ((size_t)(g & 1) * WG + r) * REC_F + (lane & 7) * 4, rec_img + (size_t)f * REC_F + (lane & 7) * 4);
                 }
             }
+#if UMR_FWD3_POS_TABLE
+            __syncwarp();  // table reads done before the next issue() rewrites it
+#endif
             cp_async_commit();
             return m;
         };

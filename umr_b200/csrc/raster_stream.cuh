@@ -116,11 +116,14 @@ __global__ void __launch_bounds__(CTA) k_bin_coarse(const float4* __restrict__ b
 // nearest (lowest face index on ties, like the ascending strict-'<' walk).  No plane is written.  Work ~ sum of bounding
 // boxes instead of pixels x candidate faces: 3x faster than k_raster_fwd3<2> at 32 x 2048^2 (profiles/r02_*).
 // ---------------------------------------------------------------------------------------------
+#ifndef UMR_VISFACES_DYNAMIC
+#define UMR_VISFACES_DYNAMIC 0   // 1: warps fetch faces from a shared counter -- built, awaiting a same-box A/B
+#endif
 __global__ void __launch_bounds__(CTA) k_visible_faces(const float* __restrict__ rec_all, const uint16_t* __restrict__ clist,
                                                        const int* __restrict__ ccount, uint8_t* __restrict__ vis, Consts K) {
     __shared__ unsigned long long s_z[CB * CB];   // 32 KB
     __shared__ float s_xp[CB], s_yp[CB];
-    __shared__ int s_bg;
+    __shared__ int s_bg, s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z, S = K.S, F = K.F;
     const int x0 = blockIdx.x * CB, y0 = blockIdx.y * CB;
@@ -135,17 +138,17 @@ __global__ void __launch_bounds__(CTA) k_visible_faces(const float* __restrict__
     for (int i = tid; i < CB * CB; i += CTA) s_z[i] = ~0ull;
     if (tid < CB) s_xp[tid] = pixel_coord(x0 + tid, S);
     else if (tid < 2 * CB) s_yp[tid - CB] = pixel_coord(S - 1 - (y0 + tid - CB), S);
-    if (tid == 0) s_bg = 0;
+    if (tid == 0) { s_bg = 0; s_next = NWARP; }
     __syncthreads();
     const uint16_t* cl = clist + cidx * F;
     const float* rec_img = rec_all + (size_t)b * F * REC_F;
-    for (int i = warp; i < nc; i += NWARP) {
+    auto scan_face = [&](int i) {
         const int f = __ldg(cl + i);
         const float* rc = rec_img + (size_t)f * REC_F;
         if (lane == 0 && i + NWARP < nc)   // the warp's next face: pull its 128-byte record into L1 while this one is scanned
             asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_img + (size_t)__ldg(cl + i + NWARP) * REC_F));
         const uint32_t flg = __float_as_uint(__ldg(rc + R_FLG));
-        if (!(K.double_side || (flg & 8u))) continue;   // back face of a single-sided render never wins (warp-uniform)
+        if (!(K.double_side || (flg & 8u))) return;   // back face of a single-sided render never wins (warp-uniform)
         // pixel rectangle to test: bounding box of the vertices widened by 2 pixels (an inside pixel lies in the box; the
         // margin covers the rounding of the index conversion), or the whole cull box for a thin face
         float xlo, xhi, ylo, yhi;
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(CTA) k_visible_faces(const float* __restrict__
         if (!(xlo == xlo && xhi == xhi && ylo == ylo && yhi == yhi)) { c0 = 0; c1 = CB; r0 = 0; r1 = CB; }  // NaN face: whole bin
         c0 = max(c0, 0); c1 = min(c1, ncol - 1); r0 = max(r0, 0); r1 = min(r1, nrow - 1);
         const int w = c1 - c0 + 1, h = r1 - r0 + 1;
-        if (w <= 0 || h <= 0) continue;   // warp-uniform
+        if (w <= 0 || h <= 0) return;   // warp-uniform
         const float i00 = __ldg(rc + R_INV + 0), i01 = __ldg(rc + R_INV + 1), i02 = __ldg(rc + R_INV + 2);
         const float i10 = __ldg(rc + R_INV + 3), i11 = __ldg(rc + R_INV + 4), i12 = __ldg(rc + R_INV + 5);
         const float i20 = __ldg(rc + R_INV + 6), i21 = __ldg(rc + R_INV + 7), i22 = __ldg(rc + R_INV + 8);
@@ -194,7 +197,19 @@ __global__ void __launch_bounds__(CTA) k_visible_faces(const float* __restrict__
             zb = (zb & 0x80000000u) ? ~zb : (zb | 0x80000000u);   // total order of floats as unsigned integers
             atomicMin(&s_z[row * CB + col], ((unsigned long long)zb << 32) | (unsigned long long)(uint32_t)f);
         }
+    };
+#if UMR_VISFACES_DYNAMIC
+    // faces are handed out dynamically (shared counter): their bounding boxes differ by an order of magnitude and a static
+    // round-robin left 27 % of the stall samples at the end-of-bin barrier (profiles/r02_C3_step_ncu_summary.txt)
+    for (int i = warp; i < nc;) {
+        scan_face(i);
+        int nx = 0;
+        if (lane == 0) nx = atomicAdd(&s_next, 1);
+        i = __shfl_sync(0xffffffffu, nx, 0);
     }
+#else
+    for (int i = warp; i < nc; i += NWARP) scan_face(i);
+#endif
     __syncthreads();
     bool bg = false;
     for (int i = tid; i < CB * CB; i += CTA) {
