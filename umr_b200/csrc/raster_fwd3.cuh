@@ -16,7 +16,7 @@ namespace umr {
 // and p2f is zero in hard mode, kernel.cu:417-431).  Same winner as RGB = 0, bit for bit.
 template <int RGB, int NC = 3>  // NC colour channels (3, or 4: the part-map render of SURVEY.md 8f-2); planes = NC + 1 (alpha)
 #ifndef UMR_FWD3_POS_TABLE
-#define UMR_FWD3_POS_TABLE 0   // 1: rank table instead of __fns in issue() -- built, awaiting a same-box A/B
+#define UMR_FWD3_POS_TABLE 1   // rank table instead of __fns in issue(): same-box A/B 0.385 -> 0.381 ms at C2 (0 restores the intrinsic)
 #endif
 #ifndef UMR_FWD3_CTAS
 #define UMR_FWD3_CTAS 4   // same-box A/B at C2: 3 CTAs (80 registers) and 5 CTAs (48 registers, 88 B of spills: 0.461 vs 0.386 ms) both lose
