@@ -12,7 +12,8 @@ T2 = 36 surface textures):
     loss.backward()  -> d/d mean_shape [V,3], d/d texture [F,T2,3];  N>1: one all-reduce of the flat
     [V*3 + F*T2*3] gradient (our one-shot peer-memory kernel inside the step's CUDA graph; NCCL fallback).
 (--config C3 adds, per BASELINE.json config 3: per-image textures sampled from a texture flow, texture-dt,
-texture-cycle on a hard render and chamfer correspondence; C5 is the 5120-face 1024x1024 sweep point.)
+texture-cycle on the hard renderer's visibility (the reference drops that render's image, loss_utils.py:327-329) and
+chamfer correspondence; C5 is the 5120-face 1024x1024 sweep point.)
 Rank 0 prints ONE JSON line.  `value` = images/s with inputs resident in HBM; `e2e` = the same step
 with that step's inputs copied from pinned host memory and the loss read back, inside the timed
 region.  `roofline` = the dominant kernel (raster forward or backward, whichever is slower): algorithmic
@@ -39,7 +40,7 @@ CONFIGS = {
                desc="CUB-like 642v/1280f mesh, 256x256 render, batch 16/GPU, silhouette+texture loss"),
     "C3": dict(subdiv=3, image_size=512, batch=32, tex_res=6, losses="full",
                desc="CUB-like 642v/1280f mesh, 512x512 render, batch 32/GPU, silhouette+texture loss on textures sampled "
-                    "from a texture flow + texture-dt + texture-cycle (hard render) + chamfer correspondence"),
+                    "from a texture flow + texture-dt + texture-cycle (hard renderer visibility) + chamfer correspondence"),
     "C5": dict(subdiv=4, image_size=1024, batch=8, tex_res=6, losses="st",
                desc="2562v/5120f mesh, 1024x1024 render, batch 8/GPU, silhouette+texture loss"),
 }
