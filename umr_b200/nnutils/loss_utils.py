@@ -201,9 +201,13 @@ class CorrLossChamfer(nn.Module):
             # one fused kernel per direction (csrc/vertex.cu k_corr_fwd / k_corr_bwd) instead of the ~250 launches of the
             # composition below: projection, per-part nearest target, weights, mean
             cache = self.__dict__.setdefault("_idx32_cache", {})
-            if str(verts.device) not in cache:
-                cache[str(verts.device)] = idx.to(torch.int32)
-            loss, vert2d = ops.corr_chamfer(verts, cams, cache[str(verts.device)], targets, self.nums, self.weights)
+            key = (str(verts.device), int(verts.shape[1]))
+            if key not in cache:
+                # checked once per (device, vertex count): the kernels gather verts[:, idx] without a bounds test of their own
+                if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= verts.shape[1]):
+                    raise IndexError("part vertex index out of range for a mesh of %d vertices" % verts.shape[1])
+                cache[key] = idx.to(torch.int32)
+            loss, vert2d = ops.corr_chamfer(verts, cams, cache[key], targets, self.nums, self.weights)
             if avg:
                 return torch.mean(loss), vert2d
             return loss
